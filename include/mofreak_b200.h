@@ -1,0 +1,167 @@
+/* mofreak_b200 — C ABI of the B200 (sm_100a) MoFREAK extraction + bag-of-words hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  The reference
+ * (ChrisWhiten/MoFREAK) has no FFI; the functions it would bind for this path are ordinary C++
+ * members, cited per entry point below as src/MoFREAK/<file>:<lines>.  The host classes in
+ * mofreak_b200/host/ (MoFREAKUtilities, MotionInterchangePatterns, BagOfWordsRepresentation) keep the
+ * reference's call surface and are implemented on top of exactly these symbols.
+ *
+ * Conventions: every function returns 0 (MFK_OK) or a negative MFK_ERR_* code and never throws; the
+ * message of the last failure on a context is mfk_last_error().  One context per GPU; a context is not
+ * thread safe (calls on one context must be serialised by the caller, as the reference's single
+ * global MoFREAKUtilities object is, main.cpp:47).  All device work is queued on the context's own
+ * non-blocking CUDA stream; functions documented "async" return before it completes.  There is no
+ * CPU fallback: if no CUDA device is usable mfk_create() fails.
+ *
+ * Fixed algorithm constants (literals in the reference): frame gap 5 (MoFREAKUtilities.cpp:378),
+ * BRISK threshold 30 and 3 octaves (:420-421, brisk.h:293), FREAK defaults (:427), 8 + 8 descriptor
+ * bytes (MoFREAKUtilities.h:20-21), MIP theta 288 on 19x19 patches (:48, :300-316).
+ */
+#ifndef MOFREAK_B200_H_
+#define MOFREAK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFK_OK              0
+#define MFK_ERR_ARG        -1   /* bad argument */
+#define MFK_ERR_CUDA       -2   /* a CUDA call failed (message has the CUDA error string) */
+#define MFK_ERR_CAPACITY   -3   /* a per-frame candidate/row budget overflowed; recreate with mfk_create_ex */
+#define MFK_ERR_NOMEM      -4
+#define MFK_ERR_STATE      -5   /* call out of order (e.g. fetch before extract) */
+
+#define MFK_FRAME_GAP       5
+
+typedef struct mfk_ctx mfk_ctx;
+
+/* One .mofreak row: the payload of struct MoFREAKFeature (MoFREAKUtilities.h:23-53) as written by
+ * writeMoFREAKFeaturesToFile (MoFREAKUtilities.cpp:691-719): x y frame scale [0 0] a0..a7 m0..m7.
+ * motion_x / motion_y are constant 0 in the reference (:476-477) and are not stored. 32 bytes. */
+typedef struct mfk_row {
+    float   x, y;
+    int32_t frame;
+    float   scale;
+    uint8_t appearance[8];
+    uint8_t motion[8];
+} mfk_row;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+
+/* Creates a context for width x height gray frames on CUDA device `device`.
+ * store_frames: capacity of the device-resident frame store (the "frame ring"), in frames.
+ * max_pairs:    how many (frame t, frame t-5) pairs one internal launch sequence processes.
+ * Replaces: new MoFREAKUtilities(dataset) + the per-frame new BriskFeatureDetector(30) / cv::FREAK
+ * construction of MoFREAKUtilities.cpp:420-427 (all tables are built once here). */
+int  mfk_create(mfk_ctx** out, int device, int width, int height, int store_frames, int max_pairs);
+/* Same, with explicit per-pair budgets (0 = default) for detector candidates and output rows. */
+int  mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_frames, int max_pairs,
+                   int cand_cap_per_pair, int row_cap_per_pair);
+void mfk_destroy(mfk_ctx* ctx);
+const char* mfk_last_error(const mfk_ctx* ctx);   /* ctx may be NULL: error of the last failed mfk_create */
+int  mfk_sync(mfk_ctx* ctx);                      /* waits for the context's stream */
+
+/* ---- frame store (the ring that keeps t and t-5 resident in HBM) ------------------------------------ */
+
+/* Copies n_frames gray u8 images (row pitch `stride` bytes, >= width) from HOST memory into store
+ * slots slot0 .. slot0+n_frames-1 (indices taken modulo store_frames).  Async when `gray` is pinned.
+ * Replaces: frame_queue.push(frame.clone()) of MoFREAKUtilities.cpp:391-399, 485-487. */
+int  mfk_upload_frames(mfk_ctx* ctx, const uint8_t* gray, size_t stride, int n_frames, int slot0);
+/* Device address of slot 0 and the store capacity, for producers that already live on the GPU
+ * (decoder output, synthetic generators).  Slots are dense: slot k starts at base + k*width*height. */
+int  mfk_frame_store(mfk_ctx* ctx, uint8_t** device_base, int* store_frames);
+
+/* ---- extraction --------------------------------------------------------------------------------- */
+
+/* Queues extraction for n_pairs frame pairs.  Pair i compares store slot cur_slot[i] with
+ * prev_slot[i] and labels its rows label[i] (the reference labels frame c of a clip c-1).
+ * Rows accumulate on the device in pair order, each pair's rows in the reference's keypoint order
+ * (BRISK layer-major, raster within a layer, minus FREAK's border drops).  Async.
+ * Replaces the loop body of MoFREAKUtilities::computeMoFREAKFromFile, MoFREAKUtilities.cpp:413-483:
+ * absdiff, BriskFeatureDetector::detect (brisk.cpp:549-704), cv::FREAK::compute,
+ * extractMotionByMotionInterchangePatterns (:288-325) and row assembly (:447-480). */
+int  mfk_extract_pairs(mfk_ctx* ctx, const int32_t* cur_slot, const int32_t* prev_slot,
+                       const int32_t* label, int n_pairs);
+/* Waits, then copies the rows accumulated since the last fetch/reset to HOST memory.
+ * rows_per_pair (optional, may be NULL) receives one count per queued pair, in queue order, at most
+ * pairs_cap entries.  *n_rows is the total; if it exceeds cap only cap rows are copied and
+ * MFK_ERR_CAPACITY is returned.  Resets the accumulation. */
+int  mfk_fetch_rows(mfk_ctx* ctx, mfk_row* rows, size_t cap, size_t* n_rows,
+                    uint32_t* rows_per_pair, size_t pairs_cap);
+/* Device-side view of the accumulated rows (valid until the next extract/fetch/reset); syncs. */
+int  mfk_rows_device(mfk_ctx* ctx, const mfk_row** device_rows, size_t* n_rows);
+int  mfk_reset_rows(mfk_ctx* ctx);
+
+/* Whole clip from HOST frames, the shape of one computeMoFREAKFromFile call
+ * (MoFREAKUtilities.cpp:374-498): uploads n_frames frames, processes frames 5..n-1 against c-5 with
+ * labels c-1, fetches the rows.  Includes H2D and D2H; this is the end-to-end path. */
+int  mfk_extract_clip(mfk_ctx* ctx, const uint8_t* gray, size_t stride, int n_frames,
+                      mfk_row* rows, size_t cap, size_t* n_rows);
+
+/* ---- MIP alone (the MotionInterchangePatterns facade) ------------------------------------------------ */
+
+/* n keypoints on one frame pair held in store slots cur_slot / prev_slot: kp_xys = n x {x, y, size}
+ * (HOST floats; x, y truncated to int exactly as at MoFREAKUtilities.cpp:460).  motion = n x 8 HOST bytes.
+ * Replaces MoFREAKUtilities::extractMotionByMotionInterchangePatterns, MoFREAKUtilities.cpp:288-325. */
+int  mfk_mip_describe(mfk_ctx* ctx, int cur_slot, int prev_slot, const float* kp_xys, int n, uint8_t* motion);
+
+/* ---- bag of words ----------------------------------------------------------------------------------- */
+
+/* codewords: K x 16 HOST bytes (8 appearance then 8 motion).  Replaces the in-memory result of
+ * BagOfWordsRepresentation::loadClusters, BagOfWordsRepresentation.cpp:140-173. */
+int  mfk_bow_set_codebook(mfk_ctx* ctx, const uint8_t* codewords, int K);
+/* desc: N x 16 HOST bytes -> idx: N HOST int32, arg-min Hamming distance, lowest index on ties.
+ * Replaces BagOfWordsRepresentation::bruteForceMatch / hammingDistance, :22-72. */
+int  mfk_bow_assign(mfk_ctx* ctx, const uint8_t* desc, size_t N, int32_t* idx);
+/* Same on DEVICE buffers (async). */
+int  mfk_bow_assign_device(mfk_ctx* ctx, const uint8_t* d_desc, size_t N, int32_t* d_idx);
+/* Assigns the rows currently accumulated on the device (descriptor = appearance|motion) and adds
+ * the per-word counts into counts[K] (HOST uint32, overwritten).  The float normalisation of
+ * buildHistogram (:125-135) is count / total on the host.  Replaces buildHistogram, :74-138. */
+int  mfk_bow_histogram_rows(mfk_ctx* ctx, uint32_t* counts);
+/* desc: N x 16 HOST bytes -> counts[K] HOST uint32 (overwritten). */
+int  mfk_bow_histogram(mfk_ctx* ctx, const uint8_t* desc, size_t N, uint32_t* counts);
+/* Optional exchange step when one video's rows live on several GPUs: sums d_counts[n] (DEVICE uint32)
+ * over all ranks of `nccl_comm` (an ncclComm_t) on the context's stream.  Async.  Returns
+ * MFK_ERR_STATE when the library was built without NCCL.  No counterpart in the reference. */
+int  mfk_allreduce_counts(mfk_ctx* ctx, uint32_t* d_counts, size_t n, void* nccl_comm);
+
+/* ---- measurement ------------------------------------------------------------------------------------ */
+
+/* CUDA-event stopwatch on the context's stream (torch.cuda.Event only sees torch's own streams). */
+int  mfk_timer_start(mfk_ctx* ctx);
+int  mfk_timer_stop(mfk_ctx* ctx, float* elapsed_ms);   /* syncs */
+/* Per-kernel accounting.  enable != 0 brackets every kernel launch with events from then on.
+ * mfk_profile_read syncs and returns, per kernel family, launches and total device ms since enable. */
+#define MFK_PROF_MAX 16
+typedef struct mfk_prof_entry { const char* name; uint32_t launches; float total_ms; } mfk_prof_entry;
+int  mfk_profile_enable(mfk_ctx* ctx, int enable);
+int  mfk_profile_read(mfk_ctx* ctx, mfk_prof_entry* entries, int cap, int* n_entries);
+/* Number of kernel launches issued by this context since creation. */
+uint64_t mfk_launch_count(const mfk_ctx* ctx);
+
+/* ---- stage access for parity tests (device -> host copies of intermediates of the LAST batch) ------- */
+/* what: 0 = pyramid image, 1 = score map S_full; layer 0..5; pair index within the last batch.
+ * out must hold the layer's width*height bytes; dims (optional) receives {width, height}. */
+int  mfk_debug_layer(mfk_ctx* ctx, int what, int layer, int pair, uint8_t* out, int* dims);
+/* Keypoints of pair `pair` of the last batch BEFORE FREAK's border filter: n x {x, y, size, response,
+ * layer} floats in reference order; writes at most cap, *n gets the full count. */
+int  mfk_debug_keypoints(mfk_ctx* ctx, int pair, float* out, int cap, int* n);
+
+/* ---- utilities that are not device work ------------------------------------------------------------- */
+
+/* Deterministic synthetic "moving squares" clip (tests, smoke, bench): n_frames of w x h starting at
+ * time t0, see mofreak_b200/host/synth.cpp. */
+void mfk_synth_clip(uint8_t* out, int w, int h, int n_frames, uint32_t seed, int t0);
+/* FREAK scale index of a keypoint size through the context-independent threshold table the device
+ * uses (exposed so tests can compare it with the libm expression it was derived from). */
+int  mfk_freak_scale_index(float kp_size);
+const char* mfk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOFREAK_B200_H_ */

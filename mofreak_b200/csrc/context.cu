@@ -1,0 +1,664 @@
+// The C ABI of include/mofreak_b200.h: context, device memory, launch sequences.  No torch, no CPU fallback.
+//
+// Device memory of a context (W x H frames, store of N frames, batches of up to F pairs):
+//   frame store            N * W*H                u8     the ring that keeps t and t-5 resident
+//   maps img/S/seen/status 4 * F * pyr_px         u8     layout in geom.h (pyr_px ~ 1.9 W*H)
+//   integral               F * (W+1)(H+1)         i32
+//   candidates             cand_cap * 30 B               ordered list + keypoint records + scans
+//   rows                   row_cap * 32 B                accumulated mfk_row output
+//   FREAK tables           8.4 MB                        64 x 256 x 43 receptive fields (float x, y, sigma)
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mofreak_b200.h"
+#include "kernels.h"
+
+using namespace mfk;
+
+static_assert(sizeof(mfk_row) == 32, "mfk_row must be 32 bytes");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum ProfId { P_ABSDIFF, P_PYRAMID, P_SCORES, P_SCAN, P_FILL, P_INTEGRAL, P_PHASE_A, P_PHASE_B, P_COMPACT, P_DESCRIBE,
+              P_BOW, P_MIP, P_COUNT };
+const char* const kProfNames[P_COUNT] = {"absdiff", "pyramid", "scores", "scan", "fill_candidates", "integral", "phase_a",
+                                         "phase_b", "compact", "describe", "bow_assign", "mip_only"};
+// kernels launched per call of each launcher family (for gpu_launches accounting)
+struct ProfSpan { int id; cudaEvent_t a, b; };
+
+}  // namespace
+
+struct mfk_ctx {
+    int device = 0, W = 0, H = 0, store_frames = 0, max_pairs = 0;
+    int cand_cap_pair = 0, row_cap_pair = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // geometry template (F filled per batch)
+    int lw[N_LAYERS], lh[N_LAYERS], rows = 0, pyr_px = 0;
+    // device buffers
+    uint8_t* store = nullptr;
+    Maps maps{};
+    int32_t* integral = nullptr;
+    CandBuf cb{};
+    uint32_t* scan_scratch = nullptr;
+    int cand_cap = 0;
+    mfk_row* rows_buf = nullptr;
+    size_t row_cap = 0;
+    uint32_t* pair_rows = nullptr;
+    int32_t *d_cur = nullptr, *d_prev = nullptr, *d_label = nullptr;
+    size_t pair_cap = 0, pairs_queued = 0;
+    DeviceTables tb{};
+    void* tb_alloc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint8_t* codebook = nullptr;
+    int K = 0;
+    uint32_t* bow_counts = nullptr;
+    int bow_counts_cap = 0;
+    void* bow_tmp = nullptr;
+    size_t bow_tmp_bytes = 0;
+    // last batch (debug access)
+    Geom last{};
+    bool have_last = false;
+    // accounting
+    uint64_t launches = 0;
+    bool prof_on = false;
+    std::vector<ProfSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    uint32_t prof_launches[P_COUNT] = {};
+    float prof_ms[P_COUNT] = {};
+    std::string err;
+};
+
+namespace {
+
+int fail(mfk_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) return fail(ctx, MFK_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+cudaEvent_t take_event(mfk_ctx* c) {
+    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct Span {          // brackets one launcher call with events when profiling is on
+    mfk_ctx* c; int id; cudaEvent_t a = nullptr, b = nullptr;
+    Span(mfk_ctx* c_, int id_, int kernels) : c(c_), id(id_) {
+        c->launches += kernels;
+        c->prof_launches[id] += kernels;
+        if (c->prof_on) { a = take_event(c); b = take_event(c); cudaEventRecord(a, c->stream); }
+    }
+    ~Span() {
+        if (a) { cudaEventRecord(b, c->stream); c->spans.push_back(ProfSpan{id, a, b}); }
+    }
+};
+
+void drain_spans(mfk_ctx* c) {
+    for (const ProfSpan& s : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) c->prof_ms[s.id] += ms;
+        c->event_pool.push_back(s.a);
+        c->event_pool.push_back(s.b);
+    }
+    c->spans.clear();
+}
+
+Geom make_geom(const mfk_ctx* c, int F) {
+    Geom g{};
+    size_t below = 0;
+    int row0 = 0;
+    static const float scale[N_LAYERS] = {1.0f, 1.5f, 2.0f, 3.0f, 4.0f, 6.0f};
+    for (int l = 0; l < N_LAYERS; l++) {
+        g.L[l].w = c->lw[l]; g.L[l].h = c->lh[l]; g.L[l].px = c->lw[l] * c->lh[l];
+        g.L[l].row0 = row0; g.L[l].base = (size_t)F * below;
+        g.L[l].scale = scale[l];
+        g.L[l].offset = (float)(0.5 * scale[l] - 0.5);
+        below += (size_t)g.L[l].px; row0 += c->lh[l];
+    }
+    g.W = c->W; g.H = c->H; g.F = F; g.rows = c->rows; g.pyr_px = c->pyr_px;
+    g.cand_cap = c->cand_cap; g.row_cap = (int)c->row_cap;
+    return g;
+}
+
+template <class T> cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T)); }
+
+int upload_tables(mfk_ctx* c) {
+    const Tables& T = tables();
+    const size_t npts = (size_t)FREAK_SCALES * FREAK_ORIENTATIONS * FREAK_POINTS;
+    FreakPoint* pts; int32_t* ps; float* thr; OrientPair* op; UsedPair* up;
+    CU(c, dalloc(&pts, npts)); c->tb_alloc[0] = pts;
+    CU(c, dalloc(&ps, FREAK_SCALES)); c->tb_alloc[1] = ps;
+    CU(c, dalloc(&thr, FREAK_SCALES)); c->tb_alloc[2] = thr;
+    CU(c, dalloc(&op, FREAK_ORIENT_PAIRS)); c->tb_alloc[3] = op;
+    CU(c, dalloc(&up, FREAK_USED_PAIRS)); c->tb_alloc[4] = up;
+    CU(c, cudaMemcpy(pts, T.points, npts * sizeof(FreakPoint), cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(ps, T.pattern_size, sizeof T.pattern_size, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(thr, T.scale_threshold, sizeof T.scale_threshold, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(op, T.orient, sizeof T.orient, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(up, T.used, sizeof T.used, cudaMemcpyHostToDevice));
+    c->tb.points = pts; c->tb.pattern_size = ps; c->tb.scale_threshold = thr; c->tb.orient = op; c->tb.used = up;
+    return MFK_OK;
+}
+
+int grow_pair_arrays(mfk_ctx* c, size_t need) {
+    if (need <= c->pair_cap) return MFK_OK;
+    size_t cap = std::max(need, c->pair_cap * 2);
+    cap = std::max<size_t>(cap, 1024);
+    CU(c, cudaStreamSynchronize(c->stream));
+    int32_t *a, *b, *l; uint32_t* pr;
+    CU(c, dalloc(&a, cap)); CU(c, dalloc(&b, cap)); CU(c, dalloc(&l, cap)); CU(c, dalloc(&pr, cap));
+    if (c->pairs_queued) {
+        CU(c, cudaMemcpy(a, c->d_cur, c->pairs_queued * 4, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(b, c->d_prev, c->pairs_queued * 4, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(l, c->d_label, c->pairs_queued * 4, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(pr, c->pair_rows, c->pairs_queued * 4, cudaMemcpyDeviceToDevice));
+    }
+    cudaFree(c->d_cur); cudaFree(c->d_prev); cudaFree(c->d_label); cudaFree(c->pair_rows);
+    c->d_cur = a; c->d_prev = b; c->d_label = l; c->pair_rows = pr; c->pair_cap = cap;
+    return MFK_OK;
+}
+
+// one launch sequence over `F` pairs whose descriptions start at pair index `first`
+int run_batch(mfk_ctx* c, size_t first, int F) {
+    const Geom g = make_geom(c, F);
+    PairList pl{c->d_cur + first, c->d_prev + first, c->d_label + first};
+    cudaStream_t st = c->stream;
+    CU(c, cudaMemsetAsync(c->cb.row_count, 0, ((size_t)F * g.rows + 1) * sizeof(uint32_t), st));
+    CU(c, cudaMemsetAsync(c->maps.seen, 0, (size_t)F * g.pyr_px, st));
+    { Span s(c, P_ABSDIFF, 1);   launch_absdiff(st, g, c->store, c->store_frames, pl, c->maps.img); }
+    { Span s(c, P_PYRAMID, 5);   launch_pyramid(st, g, c->maps.img); }
+    { Span s(c, P_SCORES, 6);    launch_scores(st, g, c->maps.img, c->maps.S, c->cb.row_count); }
+    { Span s(c, P_SCAN, 3);      launch_exclusive_scan(st, c->cb.row_count, F * g.rows, nullptr, c->scan_scratch); }
+    { Span s(c, P_FILL, 1);      launch_fill_candidates(st, g, c->maps.S, c->cb); }
+    { Span s(c, P_INTEGRAL, 2);  launch_integral(st, g, c->maps.img, c->integral); }
+    { Span s(c, P_PHASE_A, 1);   launch_phase_a(st, g, c->maps, c->cb, c->tb); }
+    { Span s(c, P_PHASE_B, 1);   launch_phase_b(st, g, c->maps, c->cb, c->tb); }
+    { Span s(c, P_COMPACT, 5);
+      launch_keep_flags(st, g, c->cb);
+      launch_exclusive_scan(st, c->cb.keep_scan, c->cand_cap, c->cb.counters + 3, c->scan_scratch);
+      launch_scatter_rows(st, g, c->cb, c->pair_rows);
+    }
+    { Span s(c, P_DESCRIBE, 2);
+      launch_describe(st, g, c->store, c->store_frames, pl, c->maps.img, c->integral, c->cb, c->tb, c->rows_buf);
+      launch_advance(st, g, c->cb);
+    }
+    CU(c, cudaGetLastError());
+    c->last = g; c->have_last = true;
+    return MFK_OK;
+}
+
+void destroy(mfk_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drain_spans(c);
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    cudaFree(c->store); cudaFree(c->maps.img); cudaFree(c->maps.S); cudaFree(c->maps.seen); cudaFree(c->maps.status);
+    cudaFree(c->integral); cudaFree(c->cb.row_count); cudaFree(c->cb.xy); cudaFree(c->cb.meta); cudaFree(c->cb.kx);
+    cudaFree(c->cb.ky); cudaFree(c->cb.ksize); cudaFree(c->cb.kresp); cudaFree(c->cb.flags); cudaFree(c->cb.scale_idx);
+    cudaFree(c->cb.keep_scan); cudaFree(c->cb.row_src); cudaFree(c->cb.counters); cudaFree(c->scan_scratch);
+    cudaFree(c->rows_buf); cudaFree(c->pair_rows); cudaFree(c->d_cur); cudaFree(c->d_prev); cudaFree(c->d_label);
+    for (void* p : c->tb_alloc) cudaFree(p);
+    cudaFree(c->codebook); cudaFree(c->bow_counts); cudaFree(c->bow_tmp);
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int ensure_bow_tmp(mfk_ctx* c, size_t bytes) {
+    if (bytes <= c->bow_tmp_bytes) return MFK_OK;
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->bow_tmp); c->bow_tmp = nullptr; c->bow_tmp_bytes = 0;
+    CU(c, cudaMalloc(&c->bow_tmp, bytes));
+    c->bow_tmp_bytes = bytes;
+    return MFK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mfk_version(void) { return "mofreak_b200 0.1 (sm_100a)"; }
+
+int mfk_freak_scale_index(float kp_size) { return scale_index_from_table(kp_size); }
+
+int mfk_create(mfk_ctx** out, int device, int width, int height, int store_frames, int max_pairs) {
+    return mfk_create_ex(out, device, width, height, store_frames, max_pairs, 0, 0);
+}
+
+int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_frames, int max_pairs, int cand_cap_pair,
+                  int row_cap_pair) {
+    if (!out) return fail(nullptr, MFK_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    // the top pyramid layer must still hold a 7x7 neighbourhood, and coordinates are packed in 16 bits
+    if (width < 48 || height < 48 || width > 8192 || height > 8192)
+        return fail(nullptr, MFK_ERR_ARG, "frame size %dx%d outside 48..8192", width, height);
+    if (store_frames < MFK_FRAME_GAP + 1 || max_pairs < 1) return fail(nullptr, MFK_ERR_ARG, "store_frames >= 6 and max_pairs >= 1 required");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MFK_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, MFK_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    mfk_ctx* c = new mfk_ctx();
+    c->device = device; c->W = width; c->H = height; c->store_frames = store_frames; c->max_pairs = max_pairs;
+#define CUC(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            fail(nullptr, MFK_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));                    \
+            destroy(c);                                                                                 \
+            return MFK_ERR_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&c->t0));
+    CUC(cudaEventCreate(&c->t1));
+    // pyramid geometry, brisk.cpp:1660, 1666
+    c->lw[0] = width; c->lh[0] = height;
+    c->lw[1] = 2 * (width / 3); c->lh[1] = 2 * (height / 3);
+    for (int l = 2; l < N_LAYERS; l++) { c->lw[l] = c->lw[l - 2] / 2; c->lh[l] = c->lh[l - 2] / 2; }
+    for (int l = 0; l < N_LAYERS; l++) { c->rows += c->lh[l]; c->pyr_px += c->lw[l] * c->lh[l]; }
+    c->cand_cap_pair = cand_cap_pair > 0 ? cand_cap_pair : std::max(4096, c->pyr_px / 6);
+    c->row_cap_pair = row_cap_pair > 0 ? row_cap_pair : std::max(1024, c->pyr_px / 48);
+    const size_t F = (size_t)max_pairs;
+    const size_t cand_cap = std::min<size_t>(F * c->cand_cap_pair, (size_t)1 << 30);
+    c->cand_cap = (int)cand_cap;
+    c->row_cap = F * c->row_cap_pair * 4;       // several batches may accumulate before a fetch
+    const size_t px = (size_t)width * height;
+    CUC(dalloc(&c->store, (size_t)store_frames * px + 64));
+    CUC(dalloc(&c->maps.img, F * c->pyr_px + 64));
+    CUC(dalloc(&c->maps.S, F * c->pyr_px + 64));
+    CUC(dalloc(&c->maps.seen, F * c->pyr_px + 64));
+    CUC(dalloc(&c->maps.status, F * c->pyr_px + 64));
+    CUC(dalloc(&c->integral, F * (size_t)(width + 1) * (height + 1)));
+    CUC(dalloc(&c->cb.row_count, F * c->rows + 2));
+    CUC(dalloc(&c->cb.xy, cand_cap)); CUC(dalloc(&c->cb.meta, cand_cap));
+    CUC(dalloc(&c->cb.kx, cand_cap)); CUC(dalloc(&c->cb.ky, cand_cap));
+    CUC(dalloc(&c->cb.ksize, cand_cap)); CUC(dalloc(&c->cb.kresp, cand_cap));
+    CUC(dalloc(&c->cb.flags, cand_cap)); CUC(dalloc(&c->cb.scale_idx, cand_cap));
+    CUC(dalloc(&c->cb.keep_scan, cand_cap + 2)); CUC(dalloc(&c->cb.row_src, cand_cap));
+    CUC(dalloc(&c->cb.counters, 8));
+    CUC(cudaMemset(c->cb.counters, 0, 8 * sizeof(uint32_t)));
+    const size_t scan_n = std::max<size_t>(cand_cap, F * c->rows);
+    CUC(dalloc(&c->scan_scratch, scan_n / 2048 + 8));
+    CUC(dalloc(&c->rows_buf, c->row_cap));
+    if (upload_tables(c) != MFK_OK) { g_create_error = c->err; destroy(c); return MFK_ERR_CUDA; }
+    if (grow_pair_arrays(c, (size_t)max_pairs) != MFK_OK) { g_create_error = c->err; destroy(c); return MFK_ERR_CUDA; }
+#undef CUC
+    *out = c;
+    return MFK_OK;
+}
+
+void mfk_destroy(mfk_ctx* ctx) { destroy(ctx); }
+
+const char* mfk_last_error(const mfk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mfk_sync(mfk_ctx* c) {
+    if (!c) return MFK_ERR_ARG;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return MFK_OK;
+}
+
+int mfk_upload_frames(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_frames, int slot0) {
+    if (!c || !gray || n_frames < 0 || slot0 < 0) return fail(c, MFK_ERR_ARG, "bad argument to mfk_upload_frames");
+    if (stride < (size_t)c->W) return fail(c, MFK_ERR_ARG, "stride %zu < width %d", stride, c->W);
+    if (n_frames > c->store_frames) return fail(c, MFK_ERR_ARG, "%d frames do not fit a store of %d", n_frames, c->store_frames);
+    CU(c, cudaSetDevice(c->device));
+    const size_t px = (size_t)c->W * c->H;
+    int done = 0;
+    while (done < n_frames) {
+        const int slot = (slot0 + done) % c->store_frames;
+        const int run = std::min(n_frames - done, c->store_frames - slot);     // contiguous slots before the wrap
+        const uint8_t* src = gray + (size_t)done * stride * c->H;
+        if (stride == (size_t)c->W)
+            CU(c, cudaMemcpyAsync(c->store + (size_t)slot * px, src, (size_t)run * px, cudaMemcpyHostToDevice, c->stream));
+        else
+            CU(c, cudaMemcpy2DAsync(c->store + (size_t)slot * px, c->W, src, stride, c->W, (size_t)run * c->H,
+                                    cudaMemcpyHostToDevice, c->stream));
+        done += run;
+    }
+    return MFK_OK;
+}
+
+int mfk_frame_store(mfk_ctx* c, uint8_t** device_base, int* store_frames) {
+    if (!c) return MFK_ERR_ARG;
+    if (device_base) *device_base = c->store;
+    if (store_frames) *store_frames = c->store_frames;
+    return MFK_OK;
+}
+
+int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_slot, const int32_t* label, int n_pairs) {
+    if (!c || n_pairs < 0 || (n_pairs && (!cur_slot || !prev_slot || !label))) return fail(c, MFK_ERR_ARG, "bad argument to mfk_extract_pairs");
+    if (n_pairs == 0) return MFK_OK;
+    CU(c, cudaSetDevice(c->device));
+    int rc = grow_pair_arrays(c, c->pairs_queued + (size_t)n_pairs);
+    if (rc != MFK_OK) return rc;
+    const size_t first = c->pairs_queued;
+    CU(c, cudaMemcpyAsync(c->d_cur + first, cur_slot, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_prev + first, prev_slot, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_label + first, label, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    for (int done = 0; done < n_pairs; done += c->max_pairs) {
+        const int F = std::min(c->max_pairs, n_pairs - done);
+        rc = run_batch(c, first + done, F);
+        if (rc != MFK_OK) return rc;
+    }
+    c->pairs_queued += (size_t)n_pairs;
+    return MFK_OK;
+}
+
+static int read_counters(mfk_ctx* c, uint32_t h[4]) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(h, c->cb.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return MFK_OK;
+}
+
+int mfk_reset_rows(mfk_ctx* c) {
+    if (!c) return MFK_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemsetAsync(c->cb.counters, 0, 4 * sizeof(uint32_t), c->stream));
+    c->pairs_queued = 0;
+    return MFK_OK;
+}
+
+int mfk_rows_device(mfk_ctx* c, const mfk_row** device_rows, size_t* n_rows) {
+    if (!c) return MFK_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    uint32_t h[4];
+    int rc = read_counters(c, h);
+    if (rc != MFK_OK) return rc;
+    if (device_rows) *device_rows = c->rows_buf;
+    if (n_rows) *n_rows = h[1];
+    if (h[0]) return fail(c, MFK_ERR_CAPACITY, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
+                          (h[0] & 1) ? "candidates " : "", (h[0] & 2) ? "rows" : "");
+    return MFK_OK;
+}
+
+int mfk_fetch_rows(mfk_ctx* c, mfk_row* rows, size_t cap, size_t* n_rows, uint32_t* rows_per_pair, size_t pairs_cap) {
+    if (!c) return MFK_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    uint32_t h[4];
+    int rc = read_counters(c, h);
+    if (rc != MFK_OK) return rc;
+    const size_t n = h[1];
+    if (n_rows) *n_rows = n;
+    const size_t ncopy = std::min(n, cap);
+    if (rows && ncopy) CU(c, cudaMemcpy(rows, c->rows_buf, ncopy * sizeof(mfk_row), cudaMemcpyDeviceToHost));
+    if (rows_per_pair) {
+        const size_t np = std::min(pairs_cap, c->pairs_queued);
+        if (np) CU(c, cudaMemcpy(rows_per_pair, c->pair_rows, np * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    const uint32_t overflow = h[0];
+    rc = mfk_reset_rows(c);
+    if (rc != MFK_OK) return rc;
+    if (overflow) return fail(c, MFK_ERR_CAPACITY, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
+                              (overflow & 1) ? "candidates " : "", (overflow & 2) ? "rows" : "");
+    if (n > cap) return fail(c, MFK_ERR_CAPACITY, "%zu rows do not fit the caller's buffer of %zu", n, cap);
+    return MFK_OK;
+}
+
+int mfk_extract_clip(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_frames, mfk_row* rows, size_t cap, size_t* n_rows) {
+    if (!c || !gray || n_frames < 0) return fail(c, MFK_ERR_ARG, "bad argument to mfk_extract_clip");
+    if (n_rows) *n_rows = 0;
+    int rc = mfk_reset_rows(c);
+    if (rc != MFK_OK) return rc;
+    if (n_frames <= MFK_FRAME_GAP) return MFK_OK;
+    // stream the clip through the store in windows that overlap by the 5-frame look-back
+    const int window = c->store_frames;
+    std::vector<int32_t> cur, prev, label;
+    int uploaded = 0;      // frames [0, uploaded) have been copied; frame k lives in slot k % window
+    int next = MFK_FRAME_GAP;
+    while (next < n_frames) {
+        // frames needed for pairs next .. last: next-5 .. last; keep at most `window` frames live
+        const int last = std::min(n_frames - 1, next - MFK_FRAME_GAP + window - 1);
+        if (uploaded <= last) {
+            rc = mfk_upload_frames(c, gray + (size_t)uploaded * stride * c->H, stride, last + 1 - uploaded, uploaded % window);
+            if (rc != MFK_OK) return rc;
+            uploaded = last + 1;
+        }
+        cur.clear(); prev.clear(); label.clear();
+        for (int k = next; k <= last; k++) { cur.push_back(k % window); prev.push_back((k - MFK_FRAME_GAP) % window); label.push_back(k - 1); }
+        rc = mfk_extract_pairs(c, cur.data(), prev.data(), label.data(), (int)cur.size());
+        if (rc != MFK_OK) return rc;
+        next = last + 1;      // the next upload reuses slots; it is ordered after these kernels by the stream
+    }
+    return mfk_fetch_rows(c, rows, cap, n_rows, nullptr, 0);
+}
+
+int mfk_mip_describe(mfk_ctx* c, int cur_slot, int prev_slot, const float* kp_xys, int n, uint8_t* motion) {
+    if (!c || n < 0 || (n && (!kp_xys || !motion)) || cur_slot < 0 || prev_slot < 0) return fail(c, MFK_ERR_ARG, "bad argument to mfk_mip_describe");
+    if (n == 0) return MFK_OK;
+    CU(c, cudaSetDevice(c->device));
+    const size_t err_off = (((size_t)n * 20 + 15) & ~(size_t)15);      // n x {3 floats} | n x 8 bytes | error word
+    int rc = ensure_bow_tmp(c, err_off + 16);
+    if (rc != MFK_OK) return rc;
+    float* d_kp = (float*)c->bow_tmp;
+    uint8_t* d_mot = (uint8_t*)c->bow_tmp + (size_t)n * 12;
+    uint32_t* d_err = (uint32_t*)((uint8_t*)c->bow_tmp + err_off);
+    CU(c, cudaMemcpyAsync(d_kp, kp_xys, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemsetAsync(d_err, 0, 4, c->stream));
+    const size_t px = (size_t)c->W * c->H;
+    { Span s(c, P_MIP, 1);
+      launch_mip_only(c->stream, c->W, c->H, c->store + (size_t)(cur_slot % c->store_frames) * px,
+                      c->store + (size_t)(prev_slot % c->store_frames) * px, d_kp, n, d_mot, d_err); }
+    uint32_t herr = 0;
+    CU(c, cudaMemcpyAsync(motion, d_mot, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (herr) return fail(c, MFK_ERR_ARG, "a keypoint's region of interest leaves the frame (cv::Mat ROI assertion in the reference)");
+    return MFK_OK;
+}
+
+// ---- bag of words --------------------------------------------------------------------------------------
+
+int mfk_bow_set_codebook(mfk_ctx* c, const uint8_t* codewords, int K) {
+    if (!c || !codewords || K < 1) return fail(c, MFK_ERR_ARG, "bad argument to mfk_bow_set_codebook");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->codebook); c->codebook = nullptr;
+    cudaFree(c->bow_counts); c->bow_counts = nullptr;
+    CU(c, cudaMalloc((void**)&c->codebook, (size_t)K * 16));
+    CU(c, dalloc(&c->bow_counts, (size_t)K));
+    CU(c, cudaMemcpy(c->codebook, codewords, (size_t)K * 16, cudaMemcpyHostToDevice));
+    c->K = K; c->bow_counts_cap = K;
+    return MFK_OK;
+}
+
+int mfk_bow_assign_device(mfk_ctx* c, const uint8_t* d_desc, size_t N, int32_t* d_idx) {
+    if (!c || (N && (!d_desc || !d_idx))) return fail(c, MFK_ERR_ARG, "bad argument to mfk_bow_assign_device");
+    if (!c->codebook) return fail(c, MFK_ERR_STATE, "no codebook set");
+    CU(c, cudaSetDevice(c->device));
+    { Span s(c, P_BOW, 1); launch_bow_assign(c->stream, d_desc, 16, N, c->codebook, c->K, d_idx, nullptr); }
+    CU(c, cudaGetLastError());
+    return MFK_OK;
+}
+
+int mfk_bow_assign(mfk_ctx* c, const uint8_t* desc, size_t N, int32_t* idx) {
+    if (!c || (N && (!desc || !idx))) return fail(c, MFK_ERR_ARG, "bad argument to mfk_bow_assign");
+    if (!c->codebook) return fail(c, MFK_ERR_STATE, "no codebook set");
+    if (N == 0) return MFK_OK;
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_bow_tmp(c, N * 20);
+    if (rc != MFK_OK) return rc;
+    uint8_t* d_desc = (uint8_t*)c->bow_tmp;
+    int32_t* d_idx = (int32_t*)((uint8_t*)c->bow_tmp + N * 16);
+    CU(c, cudaMemcpyAsync(d_desc, desc, N * 16, cudaMemcpyHostToDevice, c->stream));
+    { Span s(c, P_BOW, 1); launch_bow_assign(c->stream, d_desc, 16, N, c->codebook, c->K, d_idx, nullptr); }
+    CU(c, cudaMemcpyAsync(idx, d_idx, N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return MFK_OK;
+}
+
+int mfk_bow_histogram(mfk_ctx* c, const uint8_t* desc, size_t N, uint32_t* counts) {
+    if (!c || !counts || (N && !desc)) return fail(c, MFK_ERR_ARG, "bad argument to mfk_bow_histogram");
+    if (!c->codebook) return fail(c, MFK_ERR_STATE, "no codebook set");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemsetAsync(c->bow_counts, 0, (size_t)c->K * 4, c->stream));
+    if (N) {
+        int rc = ensure_bow_tmp(c, N * 16);
+        if (rc != MFK_OK) return rc;
+        CU(c, cudaMemcpyAsync(c->bow_tmp, desc, N * 16, cudaMemcpyHostToDevice, c->stream));
+        { Span s(c, P_BOW, 1); launch_bow_assign(c->stream, (const uint8_t*)c->bow_tmp, 16, N, c->codebook, c->K, nullptr, c->bow_counts); }
+    }
+    CU(c, cudaMemcpyAsync(counts, c->bow_counts, (size_t)c->K * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return MFK_OK;
+}
+
+int mfk_bow_histogram_rows(mfk_ctx* c, uint32_t* counts) {
+    if (!c || !counts) return fail(c, MFK_ERR_ARG, "bad argument to mfk_bow_histogram_rows");
+    if (!c->codebook) return fail(c, MFK_ERR_STATE, "no codebook set");
+    CU(c, cudaSetDevice(c->device));
+    uint32_t h[4];
+    int rc = read_counters(c, h);
+    if (rc != MFK_OK) return rc;
+    CU(c, cudaMemsetAsync(c->bow_counts, 0, (size_t)c->K * 4, c->stream));
+    if (h[1]) {
+        Span s(c, P_BOW, 1);
+        // descriptor = appearance | motion = bytes 16..31 of each 32-byte row
+        launch_bow_assign(c->stream, (const uint8_t*)c->rows_buf + 16, 32, h[1], c->codebook, c->K, nullptr, c->bow_counts);
+    }
+    CU(c, cudaMemcpyAsync(counts, c->bow_counts, (size_t)c->K * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return MFK_OK;
+}
+
+// NCCL is resolved at run time so that the library loads on machines without it and shares the copy a host
+// process (e.g. torch) has already loaded.
+int mfk_allreduce_counts(mfk_ctx* c, uint32_t* d_counts, size_t n, void* nccl_comm) {
+    if (!c || !d_counts || !nccl_comm) return fail(c, MFK_ERR_ARG, "bad argument to mfk_allreduce_counts");
+    typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    static allreduce_fn fn = nullptr;
+    if (!fn) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) fn = (allreduce_fn)dlsym(h, "ncclAllReduce");
+        if (!fn) return fail(c, MFK_ERR_STATE, "NCCL is not available (libnccl.so.2 not found)");
+    }
+    CU(c, cudaSetDevice(c->device));
+    const int ncclUint32 = 3, ncclSum = 0;      // nccl.h: ncclDataType_t / ncclRedOp_t
+    const int r = fn(d_counts, d_counts, n, ncclUint32, ncclSum, nccl_comm, c->stream);
+    if (r != 0) return fail(c, MFK_ERR_CUDA, "ncclAllReduce failed with code %d", r);
+    return MFK_OK;
+}
+
+// ---- measurement ----------------------------------------------------------------------------------------
+
+int mfk_timer_start(mfk_ctx* c) {
+    if (!c) return MFK_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventRecord(c->t0, c->stream));
+    return MFK_OK;
+}
+
+int mfk_timer_stop(mfk_ctx* c, float* elapsed_ms) {
+    if (!c || !elapsed_ms) return MFK_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventRecord(c->t1, c->stream));
+    CU(c, cudaEventSynchronize(c->t1));
+    CU(c, cudaEventElapsedTime(elapsed_ms, c->t0, c->t1));
+    return MFK_OK;
+}
+
+int mfk_profile_enable(mfk_ctx* c, int enable) {
+    if (!c) return MFK_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    drain_spans(c);
+    c->prof_on = enable != 0;
+    memset(c->prof_launches, 0, sizeof c->prof_launches);
+    memset(c->prof_ms, 0, sizeof c->prof_ms);
+    return MFK_OK;
+}
+
+int mfk_profile_read(mfk_ctx* c, mfk_prof_entry* entries, int cap, int* n_entries) {
+    if (!c || !entries || !n_entries) return MFK_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    drain_spans(c);
+    int n = 0;
+    for (int i = 0; i < P_COUNT && n < cap; i++) {
+        entries[n].name = kProfNames[i];
+        entries[n].launches = c->prof_launches[i];
+        entries[n].total_ms = c->prof_ms[i];
+        n++;
+    }
+    *n_entries = n;
+    return MFK_OK;
+}
+
+uint64_t mfk_launch_count(const mfk_ctx* c) { return c ? c->launches : 0; }
+
+// ---- stage access for parity tests ---------------------------------------------------------------------
+
+int mfk_debug_layer(mfk_ctx* c, int what, int layer, int pair, uint8_t* out, int* dims) {
+    if (!c || !out || layer < 0 || layer >= N_LAYERS || what < 0 || what > 1) return fail(c, MFK_ERR_ARG, "bad argument to mfk_debug_layer");
+    if (!c->have_last || pair < 0 || pair >= c->last.F) return fail(c, MFK_ERR_STATE, "no such pair in the last batch");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const LayerGeom& L = c->last.L[layer];
+    const uint8_t* base = (what == 0 ? c->maps.img : c->maps.S) + L.base + (size_t)pair * L.px;
+    CU(c, cudaMemcpy(out, base, (size_t)L.px, cudaMemcpyDeviceToHost));
+    if (dims) { dims[0] = L.w; dims[1] = L.h; }
+    return MFK_OK;
+}
+
+int mfk_debug_keypoints(mfk_ctx* c, int pair, float* out, int cap, int* n) {
+    if (!c || !n) return fail(c, MFK_ERR_ARG, "bad argument to mfk_debug_keypoints");
+    if (!c->have_last || pair < 0 || pair >= c->last.F) return fail(c, MFK_ERR_STATE, "no such pair in the last batch");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const Geom& g = c->last;
+    uint32_t range[2];
+    CU(c, cudaMemcpy(&range[0], c->cb.row_count + (size_t)pair * g.rows, 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(&range[1], c->cb.row_count + (size_t)(pair + 1) * g.rows, 4, cudaMemcpyDeviceToHost));
+    range[0] = std::min<uint32_t>(range[0], (uint32_t)g.cand_cap);
+    range[1] = std::min<uint32_t>(range[1], (uint32_t)g.cand_cap);
+    const size_t m = range[1] - range[0];
+    std::vector<uint8_t> flags(m);
+    std::vector<uint32_t> meta(m);
+    std::vector<float> kx(m), ky(m), ks(m), kr(m);
+    if (m) {
+        CU(c, cudaMemcpy(flags.data(), c->cb.flags + range[0], m, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(meta.data(), c->cb.meta + range[0], m * 4, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(kx.data(), c->cb.kx + range[0], m * 4, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(ky.data(), c->cb.ky + range[0], m * 4, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(ks.data(), c->cb.ksize + range[0], m * 4, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(kr.data(), c->cb.kresp + range[0], m * 4, cudaMemcpyDeviceToHost));
+    }
+    int count = 0;
+    for (size_t i = 0; i < m; i++) {
+        if (!(flags[i] & ST_KEYPOINT)) continue;
+        if (out && count < cap) {
+            out[5 * count] = kx[i]; out[5 * count + 1] = ky[i]; out[5 * count + 2] = ks[i];
+            out[5 * count + 3] = kr[i]; out[5 * count + 4] = (float)(meta[i] & 7);
+        }
+        count++;
+    }
+    *n = count;
+    return MFK_OK;
+}
+
+}  // extern "C"

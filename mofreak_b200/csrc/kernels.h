@@ -1,0 +1,69 @@
+// Launchers of the sm_100a kernels (definitions in kernels_*.cu).  All take the stream to launch on and
+// raw device pointers; none synchronises.  Buffers are described in context.cu / DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "geom.h"
+#include "tables.h"
+
+namespace mfk {
+
+struct PairList {                 // per-batch pair description (device arrays, F entries each)
+    const int32_t* cur_slot;
+    const int32_t* prev_slot;
+    const int32_t* label;
+};
+
+struct Maps {                     // F * pyr_px bytes each, layout in geom.h
+    uint8_t* img;                 // pyramid; layer 0 is |I_t - I_{t-5}|
+    uint8_t* S;                   // closed-form OAST-9/16 scores
+    uint8_t* seen;                // getScoreMaxAbove write-back marks (layers 1..5 used)
+    uint8_t* status;              // ST_* per candidate pixel (valid only where S >= threshold)
+};
+
+struct CandBuf {                  // ordered candidate list of the batch + per-candidate results
+    uint32_t* row_count;          // [F*rows + 1] hits per (pair, layer row); scanned in place -> offsets
+    uint32_t* xy;                 // x | y << 16
+    uint32_t* meta;               // pair << 3 | layer
+    float* kx; float* ky; float* ksize; float* kresp;   // refined keypoint of surviving candidates
+    uint8_t* flags;               // ST_* (ST_SURVIVE+score test passed = keypoint, ST_KEEP = output row)
+    uint8_t* scale_idx;           // FREAK scale index of kept candidates
+    uint32_t* keep_scan;          // [cand_cap + 1] exclusive scan of ST_KEEP
+    uint32_t* row_src;            // [cand_cap] candidate index of the batch's r-th output row
+    uint32_t* counters;           // [0] overflow flags (1 candidates, 2 rows), [1] rows accumulated so far,
+                                  // [2] pairs accumulated so far, [3] live candidate count of the batch
+};
+
+struct DeviceTables {             // device copies of mfk::Tables
+    const FreakPoint* points;
+    const int32_t* pattern_size;      // [64]
+    const float* scale_threshold;     // [64]
+    const OrientPair* orient;         // [45]
+    const UsedPair* used;             // [64]
+};
+
+// --- dense stage ------------------------------------------------------------------------------------
+void launch_absdiff(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, uint8_t* img);
+void launch_pyramid(cudaStream_t, const Geom&, uint8_t* img);                                  // layers 1..5
+void launch_scores(cudaStream_t, const Geom&, const uint8_t* img, uint8_t* S, uint32_t* row_count);
+void launch_fill_candidates(cudaStream_t, const Geom&, const uint8_t* S, CandBuf);
+void launch_integral(cudaStream_t, const Geom&, const uint8_t* img /*layer 0*/, int32_t* integral);
+// --- scans --------------------------------------------------------------------------------------------
+// exclusive scan of data[0..n) in place, data[n] = total; n is a host upper bound, *d_n (optional
+// device value <= n) the live length; scratch holds ceil(n/2048)+1 words
+void launch_exclusive_scan(cudaStream_t, uint32_t* data, int n, const uint32_t* d_n, uint32_t* scratch);
+// --- sparse stage -----------------------------------------------------------------------------------
+void launch_phase_a(cudaStream_t, const Geom&, Maps, CandBuf, DeviceTables);
+void launch_phase_b(cudaStream_t, const Geom&, Maps, CandBuf, DeviceTables);
+void launch_keep_flags(cudaStream_t, const Geom&, CandBuf);           // flags -> keep_scan input
+void launch_scatter_rows(cudaStream_t, const Geom&, CandBuf, uint32_t* pair_rows);   // after the scan: row_src, per-pair counts
+void launch_advance(cudaStream_t, const Geom&, CandBuf);              // counters += this batch
+void launch_describe(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, const uint8_t* img,
+                     const int32_t* integral, CandBuf, DeviceTables, void* rows /*mfk_row*/);
+void launch_mip_only(cudaStream_t, int W, int H, const uint8_t* cur, const uint8_t* prev, const float* kp_xys, int n,
+                     uint8_t* motion, uint32_t* err_flag);
+// --- bag of words --------------------------------------------------------------------------------------
+void launch_bow_assign(cudaStream_t, const uint8_t* desc, size_t stride_bytes, size_t n, const uint8_t* codebook, int K,
+                       int32_t* idx, uint32_t* counts /*nullable*/);
+
+}  // namespace mfk

@@ -1,0 +1,311 @@
+// Dense (per-pixel) stage of the extraction path, sm_100a:
+//   absdiff        cv::absdiff(current, prev)                       MoFREAKUtilities.cpp:413-414
+//   pyramid        BriskLayer::halfsample / twothirdsample          brisk.cpp:1840-2065, driven as :572-588
+//   scores         OastDetector9_16::detect + cornerScore           oast9_16.cc:46, oast9_16_nms.cc:42
+//                  (closed form of the segment test, every pixel)   + per-row hit counts
+//   candidates     ordered (pair, layer, y, x) list of hits         getAgastPoints order, brisk.cpp:1678-1690
+//   integral       cv::integral(diff)                               inside cv::FREAK::compute
+//   exclusive scan utility used for the ordered compactions
+//
+// All of this is byte/integer work bound by memory and integer-issue throughput; no stage is a dense
+// contraction, so tensor cores are not involved.
+#include "dense_device.cuh"
+#include "kernels.h"
+
+namespace mfk {
+
+// ---------------------------------------------------------------------------------------------------
+// |a - b|
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_absdiff(const uint8_t* __restrict__ store, int store_frames, const int32_t* __restrict__ cur_slot,
+                          const int32_t* __restrict__ prev_slot, uint8_t* __restrict__ img, int px, int vec_ok) {
+    const int f = blockIdx.y;
+    const uint8_t* a = store + (size_t)(cur_slot[f] % store_frames) * px;
+    const uint8_t* b = store + (size_t)(prev_slot[f] % store_frames) * px;
+    uint8_t* d = img + (size_t)f * px;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    if (vec_ok) {
+        const uint4* a4 = reinterpret_cast<const uint4*>(a);
+        const uint4* b4 = reinterpret_cast<const uint4*>(b);
+        uint4* d4 = reinterpret_cast<uint4*>(d);
+        for (int i = tid; i < px / 16; i += nthreads) {
+            const uint4 u = __ldg(a4 + i), v = __ldg(b4 + i);
+            uint4 r;
+            r.x = __vabsdiffu4(u.x, v.x); r.y = __vabsdiffu4(u.y, v.y);
+            r.z = __vabsdiffu4(u.z, v.z); r.w = __vabsdiffu4(u.w, v.w);
+            d4[i] = r;
+        }
+    } else {
+        for (int i = tid; i < px; i += nthreads) d[i] = (uint8_t)abs((int)a[i] - (int)b[i]);
+    }
+}
+
+void launch_absdiff(cudaStream_t st, const Geom& g, const uint8_t* store, int store_frames, PairList pl, uint8_t* img) {
+    const int px = g.L[0].px;
+    const int vec_ok = (px % 16 == 0);     // slots and layer-0 images then start 16-byte aligned
+    const int work = vec_ok ? px / 16 : px;
+    dim3 grid((unsigned)min((work + 255) / 256, 1024), (unsigned)g.F);
+    k_absdiff<<<grid, 256, 0, st>>>(store, store_frames, pl.cur_slot, pl.prev_slot, img, px, vec_ok);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pyramid samplers, one destination pixel per thread
+// ---------------------------------------------------------------------------------------------------
+template <bool TWOTHIRD>
+__global__ void k_downsample(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base, int sw, int spx,
+                             int dw, int dh, int dpx) {
+    const int f = blockIdx.z;
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ox >= dw || oy >= dh) return;
+    const uint8_t* src = src_base + (size_t)f * spx;
+    const int v = TWOTHIRD ? twothird_px(src, sw, ox, oy) : half_px(src, sw, ox, oy);
+    dst_base[(size_t)f * dpx + oy * dw + ox] = (uint8_t)v;
+}
+
+void launch_pyramid(cudaStream_t st, const Geom& g, uint8_t* img) {
+    // L1 = 2/3 L0; L2 = 1/2 L0; L3 = 1/2 L1; L4 = 1/2 L2; L5 = 1/2 L3   (brisk.cpp:578-587)
+    static const int SRC[6] = {-1, 0, 0, 1, 2, 3};
+    for (int l = 1; l < N_LAYERS; l++) {
+        const LayerGeom& D = g.L[l];
+        const LayerGeom& S = g.L[SRC[l]];
+        dim3 block(32, 8);
+        dim3 grid((D.w + 31) / 32, (D.h + 7) / 8, g.F);
+        if (l == 1)
+            k_downsample<true><<<grid, block, 0, st>>>(img + S.base, img + D.base, S.w, S.px, D.w, D.h, D.px);
+        else
+            k_downsample<false><<<grid, block, 0, st>>>(img + S.base, img + D.base, S.w, S.px, D.w, D.h, D.px);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// OAST-9/16 score map + per-row hit counts
+// ---------------------------------------------------------------------------------------------------
+// S_full(p) = clamp(max over the 16 arcs of 9 contiguous ring pixels of min(v_i - p) resp. min(p - v_i), minus
+// 1, to [0, 254]) — the value cornerScore's bisection converges to from b0 = 0 (oast9_16_nms.cc:42-2115), and
+// detect() at threshold b fires exactly where S_full >= b (oast9_16.cc:46).  Each pixel is staged in shared
+// memory as the pair (v, 255 - v) in the two 16-bit halves of a word, so ONE 3-input packed minimum
+// (VIMNMX3.U16x2) serves the brighter and the darker test at once:
+//     min_k v_k - p            = low  half of min_k X_k, minus p
+//     p - max_k v_k            = high half of min_k X_k, minus (255 - p)
+// 16 + 16 packed min3 build all 16 arc minima (windows of 3, then 3 of those), 8 packed max3 reduce them.
+constexpr int SC_TX = 32, SC_TY = 8, SC_HALO = 3;
+constexpr int SC_SW = SC_TX + 2 * SC_HALO, SC_SH = SC_TY + 2 * SC_HALO;
+
+__global__ void __launch_bounds__(SC_TX* SC_TY)
+k_scores(const uint8_t* __restrict__ img_base, uint8_t* __restrict__ S_base, uint32_t* __restrict__ row_count, int w, int h,
+         int px, int row0, int rows_per_pair) {
+    __shared__ uint32_t tile[SC_SH][SC_SW];
+    const int f = blockIdx.z;
+    const uint8_t* img = img_base + (size_t)f * px;
+    const int x0 = blockIdx.x * SC_TX, y0 = blockIdx.y * SC_TY;
+    const int tid = threadIdx.y * SC_TX + threadIdx.x;
+    for (int i = tid; i < SC_SH * SC_SW; i += SC_TX * SC_TY) {
+        const int sy = i / SC_SW, sx = i - sy * SC_SW;
+        const int gx = min(max(x0 + sx - SC_HALO, 0), w - 1);
+        const int gy = min(max(y0 + sy - SC_HALO, 0), h - 1);
+        const uint32_t v = img[gy * w + gx];
+        tile[sy][sx] = v | ((255u - v) << 16);
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const int cx = threadIdx.x + SC_HALO, cy = threadIdx.y + SC_HALO;
+    // ring in circle order (oast9_16.h:214-232)
+    uint32_t r[16];
+    r[0] = tile[cy][cx - 3];      r[1] = tile[cy - 1][cx - 3];  r[2] = tile[cy - 2][cx - 2];  r[3] = tile[cy - 3][cx - 1];
+    r[4] = tile[cy - 3][cx];      r[5] = tile[cy - 3][cx + 1];  r[6] = tile[cy - 2][cx + 2];  r[7] = tile[cy - 1][cx + 3];
+    r[8] = tile[cy][cx + 3];      r[9] = tile[cy + 1][cx + 3];  r[10] = tile[cy + 2][cx + 2]; r[11] = tile[cy + 3][cx + 1];
+    r[12] = tile[cy + 3][cx];     r[13] = tile[cy + 3][cx - 1]; r[14] = tile[cy + 2][cx - 2]; r[15] = tile[cy + 1][cx - 3];
+    int s = oast_score_packed(r, tile[cy][cx]);
+    const bool inside = (x >= 3 && y >= 3 && x < w - 3 && y < h - 3);
+    if (!inside) s = 0;
+    if (x < w && y < h) S_base[(size_t)f * px + y * w + x] = (uint8_t)s;
+    // one warp = one tile row: count its hits with a ballot
+    const unsigned hits = __ballot_sync(0xffffffffu, inside && s >= BRISK_THRESHOLD);
+    if (threadIdx.x == 0 && hits && y < h) atomicAdd(&row_count[(size_t)f * rows_per_pair + row0 + y], __popc(hits));
+}
+
+void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* S, uint32_t* row_count) {
+    for (int l = 0; l < N_LAYERS; l++) {
+        const LayerGeom& L = g.L[l];
+        dim3 block(SC_TX, SC_TY);
+        dim3 grid((L.w + SC_TX - 1) / SC_TX, (L.h + SC_TY - 1) / SC_TY, g.F);
+        k_scores<<<grid, block, 0, st>>>(img + L.base, S + L.base, row_count, L.w, L.h, L.px, L.row0, g.rows);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ordered candidate list: one warp per (pair, layer row), hits written at the row's scanned offset in x order
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_fill_candidates(Geom g, const uint8_t* __restrict__ S, CandBuf cb) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_rows = g.F * g.rows;
+    if (warp == 0 && lane == 0 && cb.row_count[total_rows] > (uint32_t)g.cand_cap) atomicOr(&cb.counters[0], 1u);
+    if (warp >= total_rows) return;
+    const uint32_t begin = cb.row_count[warp], end = cb.row_count[warp + 1];
+    if (begin == end) return;
+    const int f = warp / g.rows, rr = warp - f * g.rows;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < N_LAYERS; k++) l += (rr >= g.L[k].row0);
+    const LayerGeom& L = g.L[l];
+    const int y = rr - L.row0;
+    const uint8_t* row = S + L.base + (size_t)f * L.px + y * L.w;
+    uint32_t pos = begin;
+    for (int x0 = 0; x0 < L.w; x0 += 32) {
+        const int x = x0 + lane;
+        const bool hit = x < L.w && row[x] >= BRISK_THRESHOLD;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const uint32_t at = pos + __popc(m & ((1u << lane) - 1u));
+            if (at < (uint32_t)g.cand_cap) {
+                cb.xy[at] = (uint32_t)x | ((uint32_t)y << 16);
+                cb.meta[at] = ((uint32_t)f << 3) | (uint32_t)l;
+                cb.flags[at] = 0;
+            }
+        }
+        pos += __popc(m);
+    }
+}
+
+void launch_fill_candidates(cudaStream_t st, const Geom& g, const uint8_t* S, CandBuf cb) {
+    const int warps = g.F * g.rows;
+    const int blocks = (warps * 32 + 255) / 256;
+    k_fill_candidates<<<blocks, 256, 0, st>>>(g, S, cb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// integral image of the difference frame, int32 (H+1) x (W+1) with a zero top row / left column
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_integral_rows(const uint8_t* __restrict__ img, int32_t* __restrict__ integral, int W, int H, int F) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= F * (H + 1)) return;
+    const int f = warp / (H + 1), yy = warp - f * (H + 1);        // yy = output row
+    int32_t* out = integral + ((size_t)f * (H + 1) + yy) * (W + 1);
+    if (yy == 0) {
+        for (int x = lane; x <= W; x += 32) out[x] = 0;
+        return;
+    }
+    const uint8_t* row = img + (size_t)f * W * H + (size_t)(yy - 1) * W;
+    if (lane == 0) out[0] = 0;
+    int carry = 0;
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        int v = x < W ? row[x] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += n;
+        }
+        if (x < W) out[x + 1] = carry + v;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+}
+
+__global__ void k_integral_cols(int32_t* __restrict__ integral, int W, int H, int F) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= F * (W + 1)) return;
+    const int f = t / (W + 1), x = t - f * (W + 1);
+    int32_t* col = integral + (size_t)f * (H + 1) * (W + 1) + x;
+    int acc = 0;
+    for (int y = 1; y <= H; y++) {
+        acc += col[(size_t)y * (W + 1)];
+        col[(size_t)y * (W + 1)] = acc;
+    }
+}
+
+void launch_integral(cudaStream_t st, const Geom& g, const uint8_t* img, int32_t* integral) {
+    const int warps = g.F * (g.H + 1);
+    k_integral_rows<<<(warps * 32 + 255) / 256, 256, 0, st>>>(img, integral, g.W, g.H, g.F);
+    const int threads = g.F * (g.W + 1);
+    k_integral_cols<<<(threads + 127) / 128, 128, 0, st>>>(integral, g.W, g.H, g.F);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exclusive scan (three small kernels; sizes here are at most a few million words)
+// ---------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += n;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += n;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const uint32_t before = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return before + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_blocks(uint32_t* data, int n_max, const uint32_t* d_n, uint32_t* partial) {
+    const int n = d_n ? min((int)*d_n, n_max) : n_max;
+    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? data[base + k] : 0; sum += v[k]; }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(sum, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) data[base + k] = run; run += v[k]; }
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(uint32_t* partial, int n_blocks) {
+    // single block, serial over chunks of SCAN_BLOCK partials
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int c = 0; c < n_blocks; c += SCAN_BLOCK) {
+        const int base = c + threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n_blocks) ? partial[base + k] : 0; sum += v[k]; }
+        uint32_t total;
+        uint32_t run = block_exclusive_scan(sum, &total) + carry_s;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n_blocks) partial[base + k] = run; run += v[k]; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[n_blocks] = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* data, int n_max, const uint32_t* d_n, const uint32_t* partial,
+                                                           int n_blocks) {
+    const int n = d_n ? min((int)*d_n, n_max) : n_max;
+    const uint32_t add = partial[blockIdx.x];
+    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) data[base + k] += add;
+    if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = partial[n_blocks];
+}
+
+void launch_exclusive_scan(cudaStream_t st, uint32_t* data, int n, const uint32_t* d_n, uint32_t* scratch) {
+    const int n_blocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    k_scan_blocks<<<n_blocks, SCAN_THREADS, 0, st>>>(data, n, d_n, scratch);
+    k_scan_partials<<<1, SCAN_THREADS, 0, st>>>(scratch, n_blocks);
+    k_scan_add<<<n_blocks, SCAN_THREADS, 0, st>>>(data, n, d_n, scratch, n_blocks);
+}
+
+}  // namespace mfk

@@ -1,0 +1,176 @@
+// Sparse (per-candidate) stage: BriskScaleSpace::getKeypoints, reference brisk.cpp:641-703, with isMax2D
+// (:838-934) and refine3D (:937-1103), restructured so that it is order independent.
+//
+// The reference walks candidates sequentially; its lazily memoised score map makes the tie-break of isMax2D
+// depend on which scores earlier candidates happened to touch.  Here the raw map it would hold is modelled as
+//     raw(q) = S(q)                       if S(q) >= threshold (written by getAgastPoints), or
+//                                            q was read by a getScoreMaxAbove scan from the layer below, or
+//                                            q lies in the 3x3 patch of a raster-earlier candidate that survived
+//              0                           otherwise
+// (validated against the reference's object code through oracle/brisk_port.cpp, which has this same structure).
+//   phase A  one thread per candidate: 8-neighbour maximum test; candidates without an equal neighbour are
+//            decided completely (scans above/below, refinement, keypoint record);
+//   phase B  one block per pair: the few candidates with ties, layer by layer, by a fixed point whose only
+//            ordering requirement is "every raster-earlier undecided tie candidate within 3 px is final".
+#include "sparse_device.cuh"
+
+namespace mfk {
+
+// ---------------------------------------------------------------------------------------------------
+// phase A
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_phase_a(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
+    const uint32_t n = min(cb.row_count[g.F * g.rows], (uint32_t)g.cand_cap);
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const uint32_t xy = cb.xy[c], meta = cb.meta[c];
+        const int x = xy & 0xffff, y = xy >> 16, li = meta & 7;
+        PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
+        const LayerGeom& L = g.L[li];
+        const uint8_t* S = m.S + pv.off(li) + y * L.w + x;
+        // isMax2D, order-independent part (brisk.cpp:838-869): neighbours below the threshold can never exceed
+        // or equal a candidate, so the dense map can be read directly
+        const int c0 = S[0];
+        const int n0 = S[-L.w - 1], n1 = S[-L.w], n2 = S[-L.w + 1], n3 = S[-1], n4 = S[1], n5 = S[L.w - 1], n6 = S[L.w], n7 = S[L.w + 1];
+        const int mx = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
+        uint8_t* status = m.status + pv.off(li) + y * L.w + x;
+        if (mx > c0) { *status = 0; cb.flags[c] = 0; continue; }
+        if (mx == c0) { *status = ST_PENDING; cb.flags[c] = ST_PENDING; continue; }
+        after_max2d(pv, cb, tb, li, x, y, c);
+    }
+}
+
+void launch_phase_a(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTables tb) {
+    k_phase_a<<<148 * 8, 128, 0, st>>>(g, m, cb, tb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// phase B: one block per pair
+// ---------------------------------------------------------------------------------------------------
+constexpr int PB_THREADS = 128;
+constexpr int PB_LIST = 2048;      // tie candidates of one (pair, layer) staged in shared memory per sweep
+
+__global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
+    __shared__ uint32_t list[PB_LIST];
+    __shared__ uint8_t verdict[PB_LIST];
+    __shared__ int n_list, n_left, more;
+    PairView pv; pv.g = &g; pv.m = m; pv.f = blockIdx.x;
+    const uint32_t cap = (uint32_t)g.cand_cap;
+    for (int li = 0; li < N_LAYERS; li++) {
+        const LayerGeom& L = g.L[li];
+        const size_t r0 = (size_t)pv.f * g.rows + L.row0;
+        const uint32_t begin = min(cb.row_count[r0], cap), end = min(cb.row_count[r0 + L.h], cap);
+        uint32_t cursor = begin;
+        // candidates are in raster order, so taking the pending ones chunk by chunk keeps every dependency
+        // (always raster-earlier) inside the current or an already finished chunk
+        do {
+            if (threadIdx.x == 0) { n_list = 0; more = 0; }
+            __syncthreads();
+            // gather up to PB_LIST pending candidates starting at cursor, preserving order
+            uint32_t next_cursor = end;
+            for (uint32_t base = cursor; base < end; base += PB_THREADS) {
+                const uint32_t c = base + threadIdx.x;
+                const bool pend = c < end && (cb.flags[c] & ST_PENDING);
+                // ordered append: warp ballots + per-warp offsets
+                __shared__ int warp_cnt[PB_THREADS / 32];
+                const unsigned bal = __ballot_sync(0xffffffffu, pend);
+                if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(bal);
+                __syncthreads();
+                int before = n_list;
+                for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before += warp_cnt[w];
+                int total = 0;
+                for (int w = 0; w < PB_THREADS / 32; w++) total += warp_cnt[w];
+                const int slot = before + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+                const bool fits = n_list + total <= PB_LIST;
+                if (pend && fits) list[slot] = c;
+                __syncthreads();
+                if (!fits) { next_cursor = base; if (threadIdx.x == 0) more = 1; break; }
+                if (threadIdx.x == 0) n_list += total;
+                __syncthreads();
+            }
+            __syncthreads();
+            const int nl = n_list;
+            // fixed point over this chunk
+            if (threadIdx.x == 0) n_left = nl;
+            __syncthreads();
+            while (n_left > 0) {
+                for (int i = threadIdx.x; i < nl; i += PB_THREADS) {
+                    verdict[i] = 0;
+                    const uint32_t c = list[i];
+                    if (c == 0xffffffffu) continue;
+                    const uint32_t xy = cb.xy[c];
+                    const int x = xy & 0xffff, y = xy >> 16;
+                    if (earlier_pending_nearby(pv, li, x, y)) continue;
+                    verdict[i] = tie_break(pv, li, x, y) ? 2 : 1;
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < nl; i += PB_THREADS) {
+                    if (!verdict[i]) continue;
+                    const uint32_t c = list[i];
+                    const uint32_t xy = cb.xy[c];
+                    const int x = xy & 0xffff, y = xy >> 16;
+                    if (verdict[i] == 2) after_max2d(pv, cb, tb, li, x, y, c);
+                    else { pv.m.status[pv.off(li) + y * L.w + x] = 0; cb.flags[c] = 0; }
+                    list[i] = 0xffffffffu;
+                    atomicSub(&n_left, 1);
+                }
+                __threadfence_block();
+                __syncthreads();
+            }
+            cursor = next_cursor;
+            __syncthreads();
+        } while (more);
+        __threadfence();        // seen marks of layer li+1 are complete before its ties are examined
+        __syncthreads();
+    }
+}
+
+void launch_phase_b(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTables tb) {
+    k_phase_b<<<g.F, PB_THREADS, 0, st>>>(g, m, cb, tb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// keep flags -> scan input
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_keep_flags(Geom g, CandBuf cb) {
+    const uint32_t n = min(cb.row_count[g.F * g.rows], (uint32_t)g.cand_cap);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) cb.counters[3] = n;                       // live length for the scan
+    if (i < n) cb.keep_scan[i] = (cb.flags[i] & ST_KEEP) ? 1u : 0u;
+}
+
+void launch_keep_flags(cudaStream_t st, const Geom& g, CandBuf cb) {
+    k_keep_flags<<<(g.cand_cap + 255) / 256, 256, 0, st>>>(g, cb);
+}
+
+}  // namespace mfk
+
+namespace mfk {
+
+// after the scan of the keep flags: row r of the batch comes from candidate row_src[r]; rows of pair f are the
+// kept candidates between the pair's first and one-past-last candidate
+__global__ void k_scatter_rows(Geom g, CandBuf cb, uint32_t* __restrict__ pair_rows) {
+    const uint32_t n = cb.counters[3];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (cb.flags[i] & ST_KEEP)) cb.row_src[cb.keep_scan[i]] = i;
+    if (i < (uint32_t)g.F) {
+        const uint32_t b = min(cb.row_count[(size_t)i * g.rows], n), e = min(cb.row_count[(size_t)(i + 1) * g.rows], n);
+        pair_rows[cb.counters[2] + i] = cb.keep_scan[e] - cb.keep_scan[b];
+    }
+}
+
+void launch_scatter_rows(cudaStream_t st, const Geom& g, CandBuf cb, uint32_t* pair_rows) {
+    const int n = g.cand_cap > g.F ? g.cand_cap : g.F;
+    k_scatter_rows<<<(n + 255) / 256, 256, 0, st>>>(g, cb, pair_rows);
+}
+
+__global__ void k_advance(Geom g, CandBuf cb) {
+    const uint32_t rows = cb.keep_scan[cb.counters[3]];
+    const uint32_t have = cb.counters[1];
+    if (have + rows > (uint32_t)g.row_cap) { cb.counters[0] |= 2u; cb.counters[1] = (uint32_t)g.row_cap; }
+    else cb.counters[1] = have + rows;
+    cb.counters[2] += (uint32_t)g.F;
+}
+
+void launch_advance(cudaStream_t st, const Geom& g, CandBuf cb) { k_advance<<<1, 1, 0, st>>>(g, cb); }
+
+}  // namespace mfk

@@ -1,0 +1,34 @@
+// Host-built constant tables the descriptor kernel reads.  They are computed ONCE per process with the
+// host libm — the same libm the reference's CPU path would use on this machine — so that every float in
+// them is bit-identical to what cv::FREAK::buildPattern produces there (OpenCV 2.4.2 freak.cpp; the
+// reference rebuilds the table on every frame, MoFREAKUtilities.cpp:427).
+#pragma once
+#include <stdint.h>
+
+namespace mfk {
+
+enum {
+    FREAK_SCALES = 64,
+    FREAK_ORIENTATIONS = 256,
+    FREAK_POINTS = 43,
+    FREAK_ORIENT_PAIRS = 45,
+    FREAK_USED_PAIRS = 64,     // the reference keeps descriptor bytes 0..7 only (MoFREAKUtilities.cpp:453-456)
+};
+
+struct FreakPoint { float x, y, sigma; };          // offset from the keypoint and box half-size
+struct OrientPair { int16_t i, j; int32_t wdx, wdy; };
+struct UsedPair   { uint8_t i, j; };               // index = byte*8 + bit of the 8 appearance bytes
+
+struct Tables {
+    FreakPoint* points;                            // [scale][orientation][point], 704512 entries
+    int32_t     pattern_size[FREAK_SCALES];        // border a keypoint of that scale must keep
+    float       scale_threshold[FREAK_SCALES];     // [k] = smallest keypoint size whose scale index is >= k ([0] unused)
+    OrientPair  orient[FREAK_ORIENT_PAIRS];
+    UsedPair    used[FREAK_USED_PAIRS];
+};
+
+const Tables& tables();                            // built on first use, then immutable
+int scale_index_from_table(float kp_size);         // count of thresholds <= size
+int scale_index_direct(float kp_size);             // the libm expression the thresholds were derived from
+
+}  // namespace mfk
