@@ -1,0 +1,166 @@
+// Scalar device functions of the descriptor stage (FREAK orientation, receptive-field means).  Also compiles
+// as plain C++ for the CPU harness in tests/.  Compiled with -fmad=false on the device.
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include "kernels.h"
+
+namespace mfk {
+
+__device__ __forceinline__ int float_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4); return i;
+#endif
+}
+
+// atan2f exactly as glibc 2.39's libm evaluates it in float arithmetic (the Sun fdlibm scheme: argument
+// reduction against atan(0.5), atan(1), atan(1.5), atan(inf) and an odd/even split degree-11 polynomial).
+// The host's atan2f is what the reference's cv::FREAK would call on this machine; reproducing its operation
+// sequence with IEEE float ops gives the identical bit pattern for every input (checked against libm for
+// every integer pair in [-700, 700]^2 and random pairs by tests/test_device_source_cpu.py through the CPU harness).
+__device__ __forceinline__ float atanf_fdlibm(float x) {
+    const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+    const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    const float aT[11] = {3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f,
+                          9.0908870101e-02f, -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f,
+                          4.9768779427e-02f, -3.6531571299e-02f, 1.6285819933e-02f};
+    const int hx = float_bits(x);
+    const int ix = hx & 0x7fffffff;
+    int id;
+    if (ix >= 0x4c800000) return hx > 0 ? atanhi[3] + atanlo[3] : -atanhi[3] - atanlo[3];
+    if (ix < 0x3ee00000) {
+        if (ix < 0x31000000) return x;
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000) {
+            if (ix < 0x3f300000) { id = 0; x = (2.0f * x - 1.0f) / (2.0f + x); }
+            else { id = 1; x = (x - 1.0f) / (x + 1.0f); }
+        } else {
+            if (ix < 0x401c0000) { id = 2; x = (x - 1.5f) / (1.0f + 1.5f * x); }
+            else { id = 3; x = -1.0f / x; }
+        }
+    }
+    const float z = x * x;
+    const float w = z * z;
+    const float s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+    const float s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+    if (id < 0) return x - x * (s1 + s2);
+    const float r = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+    return hx < 0 ? -r : r;
+}
+
+__device__ __forceinline__ float atan2f_fdlibm(float y, float x) {
+    const float tiny = 1.0e-30f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+    const int hx = float_bits(x), hy = float_bits(y);
+    const int ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (hx == 0x3f800000) return atanf_fdlibm(y);
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+    if (iy == 0) {
+        if (m < 2) return y;
+        return m == 2 ? pi + tiny : -pi - tiny;
+    }
+    if (ix == 0) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    const int k = (iy - ix) >> 23;
+    float z;
+    if (k > 60) z = pi_o_2 + 0.5f * pi_lo;
+    else if (hx < 0 && k < -60) z = 0.0f;
+    else z = atanf_fdlibm(fabsf(y / x));
+    switch (m) {
+        case 0: return z;
+        case 1: return -z;
+        case 2: return pi - (z - pi_lo);
+        default: return (z - pi_lo) - pi;
+    }
+}
+
+// FREAK::meanIntensity: box mean around one receptive field from the (W+1)-wide integral image
+__device__ __forceinline__ int mean_intensity(const int32_t* __restrict__ I, int W1, const FreakPoint P, float kx, float ky) {
+    const float xf = P.x + kx;
+    const float yf = P.y + ky;
+    const float radius = P.sigma;
+    const int x_left = int((double)(xf - radius) + 0.5);
+    const int y_top = int((double)(yf - radius) + 0.5);
+    const int x_right = int((double)(xf + radius) + 1.5);
+    const int y_bottom = int((double)(yf + radius) + 1.5);
+    int v = I[y_bottom * W1 + x_right] - I[y_bottom * W1 + x_left] + I[y_top * W1 + x_left] - I[y_top * W1 + x_right];
+    v = v / ((x_right - x_left) * (y_bottom - y_top));
+    return v & 0xff;
+}
+
+// ---- cv::resize(ROI s x s -> 19 x 19, INTER_LINEAR, 8-bit) as OpenCV's fixed-point bilinear path computes it ----
+constexpr int PATCH = 19;
+
+struct ResizeTap {          // for destination index d along one axis
+    int16_t ofs;            // floor of the source coordinate (before clamping; used for rows)
+    int16_t by0, by1;       // row weights (fraction kept at the borders, indices clamped independently)
+    int16_t xofs;           // column index after the border collapse
+    int16_t ax0, ax1;       // column weights (an out-of-range tap collapses onto the border pixel with weight 1)
+};
+
+__device__ __forceinline__ int round_half_even(float v) {
+#ifdef __CUDA_ARCH__
+    return __float2int_rn(v);
+#else
+    return (int)lrintf(v);
+#endif
+}
+
+__device__ __forceinline__ ResizeTap resize_tap(int s, int d) {
+    ResizeTap t;
+    const double scale = (double)s / PATCH;
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int i = (int)floorf(f);
+    f -= (float)i;
+    t.ofs = (int16_t)i;
+    t.by0 = (int16_t)round_half_even((1.f - f) * 2048.f);
+    t.by1 = (int16_t)round_half_even(f * 2048.f);
+    float fx = f;
+    if (i < 0) { i = 0; fx = 0.f; }
+    if (i >= s - 1) { i = s - 1; fx = 0.f; }
+    t.xofs = (int16_t)i;
+    t.ax0 = (int16_t)round_half_even((1.f - fx) * 2048.f);
+    t.ax1 = (int16_t)round_half_even(fx * 2048.f);
+    return t;
+}
+
+// one destination pixel: 11-bit coefficients, vertical pass ((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2 >> 2
+__device__ __forceinline__ int resize_px(const uint8_t* __restrict__ roi, int stride, int s, const ResizeTap ty, const ResizeTap tx) {
+    const int y0 = min(max((int)ty.ofs, 0), s - 1), y1 = min(max((int)ty.ofs + 1, 0), s - 1);
+    const int x0 = tx.xofs, x1 = min(x0 + 1, s - 1);
+    const int R0 = roi[y0 * stride + x0] * tx.ax0 + roi[y0 * stride + x1] * tx.ax1;
+    const int R1 = roi[y1 * stride + x0] * tx.ax0 + roi[y1 * stride + x1] * tx.ax1;
+    const int v = (((ty.by0 * (R0 >> 4)) >> 16) + ((ty.by1 * (R1 >> 4)) >> 16) + 2) >> 2;
+    return min(max(v, 0), 255);
+}
+
+// SSD of motion test (centre c, shift k) on the two 19x19 patches.  Each "3x3 patch" is 9 CONSECUTIVE bytes of
+// the row-major buffer starting at the patch's top-left corner: the reference walks ROI .data linearly
+// (MoFREAKUtilities.cpp:79-88), and that is part of the output contract.  Centres :307-316, shifts :55-70.
+__device__ __forceinline__ int mip_ssd(const uint8_t* cur19, const uint8_t* prev19, int c, int k) {
+    const int CX[8] = {5, 5, 5, 9, 9, 13, 13, 13};
+    const int CY[8] = {5, 9, 13, 5, 13, 5, 9, 13};
+    const int SX[8] = {-4, -3, 0, 3, 4, 3, 0, -3};
+    const int SY[8] = {0, 3, 4, 3, 0, -3, -4, -3};
+    const uint8_t* p = cur19 + (CY[c] - 1) * PATCH + (CX[c] - 1);
+    const uint8_t* q = prev19 + (CY[c] + SY[k] - 1) * PATCH + (CX[c] + SX[k] - 1);
+    int ssd = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { const int d = (int)p[i] - (int)q[i]; ssd += d * d; }
+    return ssd;
+}
+
+// FREAK orientation bin from the two weighted gradient sums (cv::FREAK::computeImpl): the angle in degrees is
+// rounded to float, scaled in double, and truncated after adding 0.5
+__device__ __forceinline__ int freak_theta_index(int d0, int d1) {
+    const float angle = (float)((double)atan2f_fdlibm((float)d1, (float)d0) * (180.0 / 3.1415926535897932384626433832795));
+    int theta = int((double)(256.0f * angle) * (1 / 360.0) + 0.5);
+    if (theta < 0) theta += FREAK_ORIENTATIONS;
+    if (theta >= FREAK_ORIENTATIONS) theta -= FREAK_ORIENTATIONS;
+    return theta;
+}
+
+}  // namespace mfk

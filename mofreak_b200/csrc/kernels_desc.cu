@@ -7,7 +7,7 @@
 // Lanes own receptive fields (43 box means from the integral image), orientation pairs, pair tests and SSD
 // tests; bits are packed with __ballot_sync, whose lane order is laid out so that the ballot words ARE the
 // descriptor bytes.  Compiled with -fmad=false: the orientation angle must round exactly as on the host.
-#include "kernels.h"
+#include "desc_device.cuh"
 
 namespace mfk {
 
@@ -15,132 +15,27 @@ namespace {
 
 struct RowOut { float x, y; int32_t frame; float scale; uint32_t app[2]; uint32_t mot[2]; };   // == mfk_row
 
-// atan2f exactly as glibc 2.39's libm evaluates it in float arithmetic (the Sun fdlibm scheme: argument
-// reduction against atan(0.5), atan(1), atan(1.5), atan(inf) and an odd/even split degree-11 polynomial).
-// The host's atan2f is what the reference's cv::FREAK would call on this machine; reproducing its operation
-// sequence with IEEE float ops gives the identical bit pattern for every input (checked against libm for
-// every integer pair in [-700, 700]^2 and 2e7 random pairs by tests/test_host_tables.py's sibling in oracle).
-__device__ __forceinline__ float atanf_fdlibm(float x) {
-    const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
-    const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
-    const float aT[11] = {3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f,
-                          9.0908870101e-02f, -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f,
-                          4.9768779427e-02f, -3.6531571299e-02f, 1.6285819933e-02f};
-    const int hx = __float_as_int(x);
-    const int ix = hx & 0x7fffffff;
-    int id;
-    if (ix >= 0x4c800000) return hx > 0 ? atanhi[3] + atanlo[3] : -atanhi[3] - atanlo[3];
-    if (ix < 0x3ee00000) {
-        if (ix < 0x31000000) return x;
-        id = -1;
-    } else {
-        x = fabsf(x);
-        if (ix < 0x3f980000) {
-            if (ix < 0x3f300000) { id = 0; x = (2.0f * x - 1.0f) / (2.0f + x); }
-            else { id = 1; x = (x - 1.0f) / (x + 1.0f); }
-        } else {
-            if (ix < 0x401c0000) { id = 2; x = (x - 1.5f) / (1.0f + 1.5f * x); }
-            else { id = 3; x = -1.0f / x; }
-        }
-    }
-    const float z = x * x;
-    const float w = z * z;
-    const float s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
-    const float s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
-    if (id < 0) return x - x * (s1 + s2);
-    const float r = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
-    return hx < 0 ? -r : r;
-}
-
-__device__ __forceinline__ float atan2f_fdlibm(float y, float x) {
-    const float tiny = 1.0e-30f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
-    const int hx = __float_as_int(x), hy = __float_as_int(y);
-    const int ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
-    if (hx == 0x3f800000) return atanf_fdlibm(y);
-    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
-    if (iy == 0) {
-        if (m < 2) return y;
-        return m == 2 ? pi + tiny : -pi - tiny;
-    }
-    if (ix == 0) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
-    const int k = (iy - ix) >> 23;
-    float z;
-    if (k > 60) z = pi_o_2 + 0.5f * pi_lo;
-    else if (hx < 0 && k < -60) z = 0.0f;
-    else z = atanf_fdlibm(fabsf(y / x));
-    switch (m) {
-        case 0: return z;
-        case 1: return -z;
-        case 2: return pi - (z - pi_lo);
-        default: return (z - pi_lo) - pi;
-    }
-}
-
-// FREAK::meanIntensity: box mean around one receptive field from the (W+1)-wide integral image
-__device__ __forceinline__ int mean_intensity(const int32_t* __restrict__ I, int W1, const FreakPoint P, float kx, float ky) {
-    const float xf = P.x + kx;
-    const float yf = P.y + ky;
-    const float radius = P.sigma;
-    const int x_left = int((double)(xf - radius) + 0.5);
-    const int y_top = int((double)(yf - radius) + 0.5);
-    const int x_right = int((double)(xf + radius) + 1.5);
-    const int y_bottom = int((double)(yf + radius) + 1.5);
-    int v = __ldg(I + y_bottom * W1 + x_right) - __ldg(I + y_bottom * W1 + x_left) + __ldg(I + y_top * W1 + x_left) -
-            __ldg(I + y_top * W1 + x_right);
-    v = v / ((x_right - x_left) * (y_bottom - y_top));
-    return v & 0xff;
-}
-
 constexpr int DW = 8;                 // warps per block
-constexpr int PATCH = 19, PATCH_PX = 361, PATCH_PAD = 368;
+constexpr int PATCH_PX = PATCH * PATCH, PATCH_PAD = 368;
 
 struct WarpScratch {
     uint8_t cur[PATCH_PAD], prev[PATCH_PAD];
     uint8_t field[2][44];             // receptive-field means: unrotated, rotated
-    int16_t ofs[PATCH];               // source index per destination index (same for x and y before clamping)
-    int16_t ax[PATCH][2], by[PATCH][2];
-    int16_t xofs[PATCH];
+    ResizeTap tap[PATCH];             // per destination index; the same table serves rows and columns
 };
 
 // cv::resize(ROI s x s -> 19 x 19, INTER_LINEAR) for both frames into scratch (fixed-point bilinear of OpenCV's
 // imgwarp.cpp: 11-bit coefficients, vertical pass ((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2 >> 2)
 __device__ __forceinline__ void resize_roi_pair(WarpScratch& ws, const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
                                                 int W, int tl_x, int tl_y, int s, int lane) {
-    if (lane < PATCH) {
-        const double scale = (double)s / PATCH;
-        float f = (float)((lane + 0.5) * scale - 0.5);
-        int i = (int)floorf(f);
-        f -= (float)i;
-        ws.ofs[lane] = (int16_t)i;
-        ws.by[lane][0] = (int16_t)__float2int_rn((1.f - f) * 2048.f);
-        ws.by[lane][1] = (int16_t)__float2int_rn(f * 2048.f);
-        float fx = f;
-        if (i < 0) { i = 0; fx = 0.f; }
-        if (i >= s - 1) { i = s - 1; fx = 0.f; }
-        ws.xofs[lane] = (int16_t)i;
-        ws.ax[lane][0] = (int16_t)__float2int_rn((1.f - fx) * 2048.f);
-        ws.ax[lane][1] = (int16_t)__float2int_rn(fx * 2048.f);
-    }
+    if (lane < PATCH) ws.tap[lane] = resize_tap(s, lane);
     __syncwarp();
     const uint8_t* c0 = cur + (size_t)tl_y * W + tl_x;
     const uint8_t* p0 = prev + (size_t)tl_y * W + tl_x;
     for (int o = lane; o < PATCH_PX; o += 32) {
         const int dy = o / PATCH, dx = o - dy * PATCH;
-        const int y0 = min(max((int)ws.ofs[dy], 0), s - 1), y1 = min(max((int)ws.ofs[dy] + 1, 0), s - 1);
-        const int x0 = ws.xofs[dx], x1 = min(x0 + 1, s - 1);
-        const int a0 = ws.ax[dx][0], a1 = ws.ax[dx][1], b0 = ws.by[dy][0], b1 = ws.by[dy][1];
-        {
-            const int R0 = c0[y0 * W + x0] * a0 + c0[y0 * W + x1] * a1;
-            const int R1 = c0[y1 * W + x0] * a0 + c0[y1 * W + x1] * a1;
-            const int v = (((b0 * (R0 >> 4)) >> 16) + ((b1 * (R1 >> 4)) >> 16) + 2) >> 2;
-            ws.cur[o] = (uint8_t)min(max(v, 0), 255);
-        }
-        {
-            const int R0 = p0[y0 * W + x0] * a0 + p0[y0 * W + x1] * a1;
-            const int R1 = p0[y1 * W + x0] * a0 + p0[y1 * W + x1] * a1;
-            const int v = (((b0 * (R0 >> 4)) >> 16) + ((b1 * (R1 >> 4)) >> 16) + 2) >> 2;
-            ws.prev[o] = (uint8_t)min(max(v, 0), 255);
-        }
+        ws.cur[o] = (uint8_t)resize_px(c0, W, s, ws.tap[dy], ws.tap[dx]);
+        ws.prev[o] = (uint8_t)resize_px(p0, W, s, ws.tap[dy], ws.tap[dx]);
     }
     __syncwarp();
 }
@@ -150,18 +45,9 @@ __device__ __forceinline__ void resize_roi_pair(WarpScratch& ws, const uint8_t* 
 // buffer starting at the patch's top-left corner — the reference walks ROI .data linearly
 // (MoFREAKUtilities.cpp:79-88) and that is part of the output contract.
 __device__ __forceinline__ void mip_bits(const WarpScratch& ws, int lane, uint32_t out[2]) {
-    const int CX[8] = {5, 5, 5, 9, 9, 13, 13, 13};
-    const int CY[8] = {5, 9, 13, 5, 13, 5, 9, 13};
-    const int SX[8] = {-4, -3, 0, 3, 4, 3, 0, -3};
-    const int SY[8] = {0, 3, 4, 3, 0, -3, -4, -3};
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-        const int c = 4 * r + (lane >> 3), k = lane & 7;
-        const uint8_t* p = ws.cur + (CY[c] - 1) * PATCH + (CX[c] - 1);
-        const uint8_t* q = ws.prev + (CY[c] + SY[k] - 1) * PATCH + (CX[c] + SX[k] - 1);
-        int ssd = 0;
-#pragma unroll
-        for (int i = 0; i < 9; i++) { const int d = (int)p[i] - (int)q[i]; ssd += d * d; }
+        const int ssd = mip_ssd(ws.cur, ws.prev, 4 * r + (lane >> 3), lane & 7);
         out[r] = __ballot_sync(0xffffffffu, ssd > 288);
     }
 }
@@ -199,10 +85,7 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
-        const float angle = (float)((double)atan2f_fdlibm((float)d1, (float)d0) * (180.0 / 3.1415926535897932384626433832795));
-        int theta = int((double)(256.0f * angle) * (1 / 360.0) + 0.5);
-        if (theta < 0) theta += FREAK_ORIENTATIONS;
-        if (theta >= FREAK_ORIENTATIONS) theta -= FREAK_ORIENTATIONS;
+        const int theta = freak_theta_index(d0, d1);
 
         // --- FREAK: the 64 pair tests the reference keeps ---
         const FreakPoint* PT = P0 + (size_t)theta * FREAK_POINTS;

@@ -30,6 +30,7 @@ static inline uint32_t __vimax3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
 
 #include "../mofreak_b200/csrc/dense_device.cuh"
 #include "../mofreak_b200/csrc/sparse_device.cuh"
+#include "../mofreak_b200/csrc/desc_device.cuh"
 
 using namespace mfk;
 
@@ -180,6 +181,84 @@ void hh_layer(const uint8_t* diff, int w, int h, int layer, uint8_t* img_out, ui
     memcpy(img_out, H.img.data() + L.base, L.px);
     memcpy(score_out, H.S.data() + L.base, L.px);
     dims[0] = L.w; dims[1] = L.h;
+}
+
+// The whole per-pair path with the device functions: rows (32 bytes each, mfk_row layout) in reference order.
+int hh_extract_pair(const uint8_t* cur, const uint8_t* prev, int w, int h, int label, uint8_t* rows_out, int cap) {
+    std::vector<uint8_t> diff((size_t)w * h);
+    for (size_t i = 0; i < diff.size(); i++) diff[i] = (uint8_t)abs((int)cur[i] - (int)prev[i]);
+    Harness H;
+    H.setup(w, h);
+    H.dense(diff.data());
+    H.sparse(false);
+    const int W1 = w + 1;
+    std::vector<int32_t> I((size_t)W1 * (h + 1), 0);
+    for (int y = 0; y < h; y++) {
+        int run = 0;
+        for (int x = 0; x < w; x++) { run += diff[(size_t)y * w + x]; I[(size_t)(y + 1) * W1 + x + 1] = I[(size_t)y * W1 + x + 1] + run; }
+    }
+    int n = 0;
+    for (size_t c = 0; c < H.xy.size(); c++) {
+        if (!(H.flags[c] & ST_KEEP)) continue;
+        const float kx = H.kx[c], ky = H.ky[c], ksize = H.ksize[c];
+        const int sidx = H.scale_idx[c];
+        const FreakPoint* P0 = H.tb.points + (size_t)sidx * FREAK_ORIENTATIONS * FREAK_POINTS;
+        uint8_t field[FREAK_POINTS];
+        for (int p = 0; p < FREAK_POINTS; p++) field[p] = (uint8_t)mean_intensity(I.data(), W1, P0[p], kx, ky);
+        int d0 = 0, d1 = 0;
+        for (int q = 0; q < FREAK_ORIENT_PAIRS; q++) {
+            const OrientPair op = H.tb.orient[q];
+            const int delta = (int)field[op.i] - (int)field[op.j];
+            d0 += delta * op.wdx / 2048;
+            d1 += delta * op.wdy / 2048;
+        }
+        const int theta = freak_theta_index(d0, d1);
+        const FreakPoint* PT = P0 + (size_t)theta * FREAK_POINTS;
+        for (int p = 0; p < FREAK_POINTS; p++) field[p] = (uint8_t)mean_intensity(I.data(), W1, PT[p], kx, ky);
+        uint8_t app[8] = {0}, mot[8] = {0};
+        for (int i = 0; i < 64; i++) if (field[H.tb.used[i].i] >= field[H.tb.used[i].j]) app[i >> 3] |= (uint8_t)(1u << (i & 7));
+        const int xi = (int)kx, yi = (int)ky, half = (int)ksize / 2, side = (int)ceilf(ksize);
+        uint8_t a19[PATCH * PATCH], b19[PATCH * PATCH];
+        ResizeTap tap[PATCH];
+        for (int d = 0; d < PATCH; d++) tap[d] = resize_tap(side, d);
+        const uint8_t* c0 = cur + (size_t)(yi - half) * w + (xi - half);
+        const uint8_t* p0 = prev + (size_t)(yi - half) * w + (xi - half);
+        for (int o = 0; o < PATCH * PATCH; o++) {
+            a19[o] = (uint8_t)resize_px(c0, w, side, tap[o / PATCH], tap[o % PATCH]);
+            b19[o] = (uint8_t)resize_px(p0, w, side, tap[o / PATCH], tap[o % PATCH]);
+        }
+        for (int i = 0; i < 64; i++) if (mip_ssd(a19, b19, i >> 3, i & 7) > 288) mot[i >> 3] |= (uint8_t)(1u << (i & 7));
+        if (n < cap) {
+            uint8_t* r = rows_out + (size_t)32 * n;
+            const int32_t frame = label;
+            memcpy(r, &kx, 4); memcpy(r + 4, &ky, 4); memcpy(r + 8, &frame, 4); memcpy(r + 12, &ksize, 4);
+            memcpy(r + 16, app, 8); memcpy(r + 24, mot, 8);
+        }
+        n++;
+    }
+    return n;
+}
+
+float hh_atan2f(float y, float x) { return atan2f_fdlibm(y, x); }
+int hh_theta_index(int d0, int d1) { return freak_theta_index(d0, d1); }
+int hh_scale_index_table(float size) { return scale_index_from_table(size); }
+int hh_scale_index_direct(float size) { return scale_index_direct(size); }
+// counts mismatches of the device atan2f against the host libm over a grid and random integer pairs
+long hh_atan2f_sweep(int grid, long random_pairs, unsigned seed) {
+    long bad = 0;
+    for (int a = -grid; a <= grid; a++)
+        for (int b = -grid; b <= grid; b++) {
+            const float r = atan2f((float)a, (float)b), q = atan2f_fdlibm((float)a, (float)b);
+            if (memcmp(&r, &q, 4) != 0) bad++;
+        }
+    unsigned s = seed ? seed : 1u;
+    for (long i = 0; i < random_pairs; i++) {
+        s = s * 1664525u + 1013904223u; const int a = (int)((s >> 8) % 400001u) - 200000;
+        s = s * 1664525u + 1013904223u; const int b = (int)((s >> 8) % 400001u) - 200000;
+        const float r = atan2f((float)a, (float)b), q = atan2f_fdlibm((float)a, (float)b);
+        if (memcmp(&r, &q, 4) != 0) bad++;
+    }
+    return bad;
 }
 
 }  // extern "C"

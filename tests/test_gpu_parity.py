@@ -1,0 +1,247 @@
+"""GPU parity proper: everything goes through the C ABI (ctypes) and is compared with the CPU oracle on the same
+seeded inputs and with the committed golden fixtures; full-size cases use size-independent properties.
+Bar: bit-exact — keypoint coordinates are float32 but must be IDENTICAL (tolerance 0), as are all descriptor
+bytes and bag-of-words indices."""
+import numpy as np
+import pytest
+
+import mofreak_b200
+from mofreak_b200 import sharding
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+CASES = util.golden_cases()
+
+
+@pytest.fixture(scope="module")
+def lib_loaded():
+    import os
+    L = mofreak_b200.lib()
+    assert os.path.samefile(mofreak_b200.LIB_PATH, os.path.join(os.path.dirname(mofreak_b200.__file__), "libmofreak_b200.so"))
+    return L
+
+
+def run_clip(clip, max_pairs=8, store=None):
+    n, h, w = clip.shape
+    with mofreak_b200.Context(w, h, store or max(16, n), max_pairs) as ctx:
+        rows = ctx.extract_clip(clip)
+        assert ctx.launch_count() > 0 or n <= 5
+    return rows
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_rows_bit_exact(lib_loaded, orc, name):
+    c = CASES[name]
+    clip = mofreak_b200.synth_clip(c["width"], c["height"], c["frames"], c["seed"])
+    got = run_clip(clip, max_pairs=16)
+    want = util.golden_rows(name)
+    assert util.rows_equal(got, want), util.describe_diff(got, want)
+    assert orc.format_mofreak(got) == util.golden_text(name)
+
+
+@pytest.mark.parametrize("shape,frames,seed", [((160, 120), 14, 11), ((320, 240), 9, 12), ((720, 576), 7, 13),
+                                               ((106, 97), 9, 14), ((367, 251), 8, 15), ((48, 48), 8, 16), ((1280, 720), 6, 17)])
+def test_rows_equal_oracle(orc, shape, frames, seed):
+    w, h = shape
+    clip = mofreak_b200.synth_clip(w, h, frames, seed)
+    got = run_clip(clip)
+    want = orc.extract_clip(clip)
+    assert util.rows_equal(got, want), util.describe_diff(got, want)
+
+
+def test_stages_equal_oracle(orc):
+    w, h, n = 212, 163, 8
+    clip = mofreak_b200.synth_clip(w, h, n, 21)
+    with mofreak_b200.Context(w, h, 16, 8) as ctx:
+        ctx.upload_frames(clip, 0)
+        cur = np.arange(5, n)
+        ctx.extract_pairs(cur, cur - 5, cur - 1)
+        for pair, (c, d) in enumerate(util.diff_frames(clip)):
+            layers = [d, orc.twothirdsample(d), orc.halfsample(d)]
+            layers.append(orc.halfsample(layers[1])); layers.append(orc.halfsample(layers[2])); layers.append(orc.halfsample(layers[3]))
+            for li, want in enumerate(layers):
+                assert np.array_equal(ctx.debug_layer(0, li, pair), want), "pyramid layer %d" % li
+                assert np.array_equal(ctx.debug_layer(1, li, pair), orc.score_map(want)), "score map layer %d" % li
+            assert util.kp_equal(ctx.debug_keypoints(pair), orc.brisk(d))
+        rows, per_pair = ctx.fetch_rows(100000, n - 5)
+        assert per_pair.sum() == len(rows)
+        want = orc.extract_clip(clip)
+        assert util.rows_equal(rows, want)
+        assert [int((want["frame"] == c - 1).sum()) for c in range(5, n)] == list(per_pair)
+
+
+def test_tie_heavy_frames(orc):
+    """Quantised noise: thousands of equal-score neighbours, the order-dependent part of the reference's NMS."""
+    rng = np.random.default_rng(31)
+    w, h = 128, 96
+    frames = np.zeros((7, h, w), np.uint8)
+    frames[5] = (rng.integers(0, 4, (h, w)) * 80).astype(np.uint8)
+    frames[6] = np.kron(rng.integers(0, 3, (h // 4, w // 4)) * 100, np.ones((4, 4))).astype(np.uint8)
+    with mofreak_b200.Context(w, h, 16, 4, cand_cap_per_pair=w * h * 2, row_cap_per_pair=w * h) as ctx:
+        ctx.upload_frames(frames, 0)
+        ctx.extract_pairs([5, 6], [0, 1], [4, 5])
+        for pair, c in enumerate((5, 6)):
+            want = orc.brisk(frames[c])          # prev frame is zero, so the diff image is the frame itself
+            assert len(want) > 50
+            assert util.kp_equal(ctx.debug_keypoints(pair), want)
+        rows, _ = ctx.fetch_rows(200000)
+    assert util.rows_equal(rows, orc.extract_clip(frames))
+
+
+def test_empty_ragged_and_blank_inputs(orc):
+    clip = mofreak_b200.synth_clip(160, 120, 9, 41)
+    with mofreak_b200.Context(160, 120, 16, 8) as ctx:
+        for n in (0, 1, 5):
+            assert len(ctx.extract_clip(clip[:n])) == 0                      # no frame pair exists yet
+        assert util.rows_equal(ctx.extract_clip(clip[:6]), orc.extract_clip(clip[:6]))
+        blank = np.zeros((8, 120, 160), np.uint8)
+        assert len(ctx.extract_clip(blank)) == 0
+        still = np.repeat(clip[:1], 8, axis=0)                               # no motion -> zero difference image
+        assert len(ctx.extract_clip(still)) == 0
+        ctx.extract_pairs([], [], [])
+        rows, per = ctx.fetch_rows(10, 0)
+        assert len(rows) == 0
+
+
+def test_batching_and_windowing_do_not_change_rows(orc):
+    clip = mofreak_b200.synth_clip(160, 120, 40, 51)
+    want = orc.extract_clip(clip)
+    for max_pairs, store in ((1, 6), (3, 7), (7, 13), (64, 64)):
+        got = run_clip(clip, max_pairs=max_pairs, store=store)      # store < clip length: ring reuse with the 5-frame look-back
+        assert util.rows_equal(got, want), "max_pairs=%d store=%d: %s" % (max_pairs, store, util.describe_diff(got, want))
+
+
+def test_ring_wraparound_and_arbitrary_pair_order(orc):
+    clip = mofreak_b200.synth_clip(160, 120, 12, 61)
+    with mofreak_b200.Context(160, 120, 16, 5) as ctx:
+        ctx.upload_frames(clip, 10)                                  # slots 10..15, 0..5
+        cur = np.array([11, 5, 8, 8], np.int32)
+        ctx.extract_pairs((cur + 10) % 16, (cur - 5 + 10) % 16, cur - 1)
+        rows, per = ctx.fetch_rows(100000, 4)
+    want = orc.extract_clip(clip)
+    parts = [want[want["frame"] == c - 1] for c in cur]
+    assert list(per) == [len(p) for p in parts]
+    assert util.rows_equal(rows, np.concatenate(parts))
+
+
+def test_capacity_overflow_is_reported_not_silent():
+    clip = mofreak_b200.synth_clip(320, 240, 7, 71)
+    with mofreak_b200.Context(320, 240, 16, 2, cand_cap_per_pair=64, row_cap_per_pair=8) as ctx:
+        with pytest.raises(mofreak_b200.MofreakError) as e:
+            ctx.extract_clip(clip)
+        assert e.value.code == mofreak_b200.capi.MFK_ERR_CAPACITY
+
+
+def test_mip_facade(orc):
+    clip = mofreak_b200.synth_clip(320, 240, 6, 81)
+    rng = np.random.default_rng(82)
+    kps = np.stack([rng.uniform(60, 260, 200), rng.uniform(60, 180, 200), rng.uniform(8.4, 100, 200)], 1).astype(np.float32)
+    with mofreak_b200.Context(320, 240, 8, 1) as ctx:
+        ctx.upload_frames(clip, 0)
+        got = ctx.mip_describe(5, 0, kps)
+        want = np.stack([orc.mip_extract(clip[5], clip[0], float(s), int(x), int(y)) for x, y, s in kps])
+        assert np.array_equal(got, want)
+        with pytest.raises(mofreak_b200.MofreakError):
+            ctx.mip_describe(5, 0, np.array([[3.0, 3.0, 40.0]], np.float32))     # ROI leaves the frame
+
+
+@pytest.mark.parametrize("K", [1, 2, 600, 1000, 10100, 20000])
+def test_bow_assignment_and_histogram(orc, K):
+    rng = np.random.default_rng(K)
+    cb = rng.integers(0, 256, (K, 16), dtype=np.uint8)
+    if K > 20:
+        cb[K // 2] = cb[3]; cb[K - 1] = cb[3]                      # duplicates: the lowest index must win
+    desc = rng.integers(0, 256, (5000, 16), dtype=np.uint8)
+    desc[:min(K, 600)] = cb[:min(K, 600)]
+    desc[700] = cb[K - 1]
+    with mofreak_b200.Context(160, 120, 8, 1) as ctx:
+        ctx.bow_set_codebook(cb)
+        idx = ctx.bow_assign(desc)
+        want = orc.bow_assign(desc[:800], cb) if K > 5000 else orc.bow_assign(desc, cb)
+        assert np.array_equal(idx[:len(want)], want)
+        dist = lambda d, k: int(np.unpackbits(d ^ cb[k]).sum())    # property check on the rest: it is an arg-min
+        for i in range(len(want), len(desc), 97):
+            best = dist(desc[i], idx[i])
+            sample = rng.integers(0, K, 200)
+            assert all(dist(desc[i], int(k)) > best or (dist(desc[i], int(k)) == best and k >= idx[i]) for k in sample)
+        assert np.array_equal(ctx.bow_histogram(desc), np.bincount(idx, minlength=K))
+        assert not ctx.bow_histogram(desc[:0]).any()
+        assert len(ctx.bow_assign(desc[:0])) == 0
+
+
+def test_bow_on_device_rows(orc):
+    clip = mofreak_b200.synth_clip(320, 240, 9, 91)
+    rng = np.random.default_rng(92)
+    cb = rng.integers(0, 256, (600, 16), dtype=np.uint8)
+    with mofreak_b200.Context(320, 240, 16, 4) as ctx:
+        ctx.bow_set_codebook(cb)
+        ctx.upload_frames(clip, 0)
+        cur = np.arange(5, 9)
+        ctx.extract_pairs(cur, cur - 5, cur - 1)
+        counts = ctx.bow_histogram_rows()
+        rows, _ = ctx.fetch_rows(100000)
+    desc = np.concatenate([rows["appearance"], rows["motion"]], 1)
+    assert np.array_equal(counts, np.bincount(orc.bow_assign(desc, cb), minlength=600))
+    # the text path of the reference (buildHistogram on the .mofreak file) gives the same normalised histogram
+    ok, hist = orc.build_histogram(orc.format_mofreak(rows), cb)
+    assert ok and np.array_equal(hist, counts.astype(np.float32) / np.float32(counts.sum()))
+
+
+def test_full_size_properties_trecvid_shape():
+    """BASELINE configs[3] at bench size is too big for the CPU oracle; check what must hold at any size:
+    determinism, independence from batch composition, frame-range sharding with the 5-frame halo, and the
+    per-pair accounting."""
+    w, h, n = 720, 576, 37
+    clip = mofreak_b200.synth_clip(w, h, n, 101)
+    with mofreak_b200.Context(w, h, n, 32) as ctx:
+        a = ctx.extract_clip(clip)
+        b = ctx.extract_clip(clip)
+        assert util.rows_equal(a, b) and len(a) > 20000
+        ctx.upload_frames(clip, 0)
+        order = np.arange(5, n)[::-1].copy()                        # reversed pair order, different batch composition
+        ctx.extract_pairs(order, order - 5, order - 1)
+        rows, per = ctx.fetch_rows(len(a) + 10, len(order))
+        assert per.sum() == len(a)
+        back = np.concatenate([rows[per[:i].sum():per[:i + 1].sum()] for i in range(len(order))][::-1])
+        assert util.rows_equal(back, a)
+    parts = []
+    for first, lo, hi in sharding.shard_stream(n, 4):               # what 4 GPUs would each do
+        with mofreak_b200.Context(w, h, 16, 8) as ctx:
+            r = ctx.extract_clip(clip[first:hi])
+            r["frame"] += first
+            parts.append(r)
+    assert util.rows_equal(np.concatenate(parts), a)
+    assert np.all(np.diff(a["frame"]) >= 0) and a["frame"].min() == 4 and a["frame"].max() == n - 2
+
+
+def test_full_size_properties_kth_batch():
+    """BASELINE configs[1] shape: many small clips in one batch; rows of a clip must not depend on its neighbours."""
+    clips = [mofreak_b200.synth_clip(160, 120, 30, 200 + i) for i in range(24)]
+    with mofreak_b200.Context(160, 120, 24 * 30, 512) as ctx:
+        alone = [ctx.extract_clip(c) for c in clips[:3]]
+        ctx.upload_frames(np.concatenate(clips), 0)
+        cur = np.concatenate([np.arange(5, 30) + 30 * i for i in range(24)])
+        lab = np.concatenate([np.arange(5, 30) - 1 for _ in range(24)])
+        ctx.extract_pairs(cur, cur - 5, lab)
+        rows, per = ctx.fetch_rows(1 << 20, len(cur))
+    per_clip = per.reshape(24, 25).sum(1)
+    offs = np.concatenate([[0], np.cumsum(per_clip)]).astype(np.int64)
+    for i in range(3):
+        assert util.rows_equal(rows[offs[i]:offs[i + 1]], alone[i])
+    assert per.sum() == len(rows)
+
+
+def test_timer_and_profile_hooks():
+    clip = mofreak_b200.synth_clip(160, 120, 9, 301)
+    with mofreak_b200.Context(160, 120, 16, 4) as ctx:
+        ctx.upload_frames(clip, 0)
+        ctx.profile_enable(True)
+        before = ctx.launch_count()
+        ctx.timer_start()
+        cur = np.arange(5, 9)
+        ctx.extract_pairs(cur, cur - 5, cur - 1)
+        ms = ctx.timer_stop()
+        prof = ctx.profile_read()
+        assert ms > 0 and ctx.launch_count() - before == 27
+        assert prof["scores"][0] == 6 and prof["scores"][1] > 0 and prof["describe"][1] > 0
