@@ -28,10 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H = 720, 576
-STREAMS = 8                 # per GPU
+STREAMS = 16                # per GPU
 PAIRS_PER_STREAM = 64
 FRAMES_PER_STREAM = PAIRS_PER_STREAM + 5
-MAX_PAIRS = 64              # pairs per internal launch sequence
+MAX_PAIRS = 256             # pairs per internal launch sequence
 METRIC = "frames_per_sec_720x576"
 UNIT = "frames/s"
 
@@ -304,12 +304,16 @@ def run_ours(args):
 
 
 def main():
+    global STREAMS, MAX_PAIRS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=STREAMS, help="720x576 streams per GPU per step")
+    ap.add_argument("--max-pairs", type=int, default=MAX_PAIRS, help="frame pairs per internal launch sequence")
     args = ap.parse_args()
+    STREAMS, MAX_PAIRS = args.streams, args.max_pairs
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -186,6 +186,7 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
     cudaStream_t st = c->stream;
     CU(c, cudaMemsetAsync(c->cb.row_count, 0, ((size_t)F * g.rows + 1) * sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(c->maps.seen, 0, (size_t)F * g.pyr_px, st));
+    CU(c, cudaMemsetAsync(c->cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
     { Span s(c, P_ABSDIFF, 1);   launch_absdiff(st, g, c->store, c->store_frames, pl, c->maps.img); }
     { Span s(c, P_PYRAMID, 5);   launch_pyramid(st, g, c->maps.img); }
     { Span s(c, P_SCORES, 6);    launch_scores(st, g, c->maps.img, c->maps.S, c->cb.row_count); }
@@ -217,7 +218,7 @@ void destroy(mfk_ctx* c) {
     cudaFree(c->store); cudaFree(c->maps.img); cudaFree(c->maps.S); cudaFree(c->maps.seen); cudaFree(c->maps.status);
     cudaFree(c->integral); cudaFree(c->cb.row_count); cudaFree(c->cb.xy); cudaFree(c->cb.meta); cudaFree(c->cb.kx);
     cudaFree(c->cb.ky); cudaFree(c->cb.ksize); cudaFree(c->cb.kresp); cudaFree(c->cb.flags); cudaFree(c->cb.scale_idx);
-    cudaFree(c->cb.keep_scan); cudaFree(c->cb.row_src); cudaFree(c->cb.counters); cudaFree(c->scan_scratch);
+    cudaFree(c->cb.keep_scan); cudaFree(c->cb.row_src); cudaFree(c->cb.pend_count); cudaFree(c->cb.pend_list); cudaFree(c->cb.counters); cudaFree(c->scan_scratch);
     cudaFree(c->rows_buf); cudaFree(c->pair_rows); cudaFree(c->d_cur); cudaFree(c->d_prev); cudaFree(c->d_label);
     for (void* p : c->tb_alloc) cudaFree(p);
     cudaFree(c->codebook); cudaFree(c->bow_counts); cudaFree(c->bow_tmp);
@@ -300,6 +301,8 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     CUC(dalloc(&c->cb.ksize, cand_cap)); CUC(dalloc(&c->cb.kresp, cand_cap));
     CUC(dalloc(&c->cb.flags, cand_cap)); CUC(dalloc(&c->cb.scale_idx, cand_cap));
     CUC(dalloc(&c->cb.keep_scan, cand_cap + 2)); CUC(dalloc(&c->cb.row_src, cand_cap));
+    CUC(dalloc(&c->cb.pend_count, F * N_LAYERS));
+    CUC(dalloc(&c->cb.pend_list, F * N_LAYERS * PEND_CAP));
     CUC(dalloc(&c->cb.counters, 8));
     CUC(cudaMemset(c->cb.counters, 0, 8 * sizeof(uint32_t)));
     const size_t scan_n = std::max<size_t>(cand_cap, F * c->rows);

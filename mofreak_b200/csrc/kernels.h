@@ -30,9 +30,13 @@ struct CandBuf {                  // ordered candidate list of the batch + per-c
     uint8_t* scale_idx;           // FREAK scale index of kept candidates
     uint32_t* keep_scan;          // [cand_cap + 1] exclusive scan of ST_KEEP
     uint32_t* row_src;            // [cand_cap] candidate index of the batch's r-th output row
+    uint32_t* pend_count;         // [F*6] tie candidates per (pair, layer), appended by phase A
+    uint32_t* pend_list;          // [F*6][PEND_CAP] their candidate indices (unordered)
     uint32_t* counters;           // [0] overflow flags (1 candidates, 2 rows), [1] rows accumulated so far,
                                   // [2] pairs accumulated so far, [3] live candidate count of the batch
 };
+
+enum { PEND_CAP = 2048 };         // per (pair, layer); beyond it phase B falls back to an ordered sweep
 
 struct DeviceTables {             // device copies of mfk::Tables
     const FreakPoint* points;

@@ -34,7 +34,12 @@ __global__ void __launch_bounds__(128) k_phase_a(const __grid_constant__ Geom g,
         const int mx = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
         uint8_t* status = m.status + pv.off(li) + y * L.w + x;
         if (mx > c0) { *status = 0; cb.flags[c] = 0; continue; }
-        if (mx == c0) { *status = ST_PENDING; cb.flags[c] = ST_PENDING; continue; }
+        if (mx == c0) {
+            *status = ST_PENDING; cb.flags[c] = ST_PENDING;
+            const uint32_t slot = atomicAdd(&cb.pend_count[pv.f * N_LAYERS + li], 1u);
+            if (slot < PEND_CAP) cb.pend_list[(size_t)(pv.f * N_LAYERS + li) * PEND_CAP + slot] = c;
+            continue;
+        }
         after_max2d(pv, cb, tb, li, x, y, c);
     }
 }
@@ -47,7 +52,7 @@ void launch_phase_a(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTa
 // phase B: one block per pair
 // ---------------------------------------------------------------------------------------------------
 constexpr int PB_THREADS = 128;
-constexpr int PB_LIST = 2048;      // tie candidates of one (pair, layer) staged in shared memory per sweep
+constexpr int PB_LIST = PEND_CAP;  // tie candidates of one (pair, layer) staged in shared memory per sweep
 
 __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
     __shared__ uint32_t list[PB_LIST];
@@ -60,13 +65,21 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
         const size_t r0 = (size_t)pv.f * g.rows + L.row0;
         const uint32_t begin = min(cb.row_count[r0], cap), end = min(cb.row_count[r0 + L.h], cap);
         uint32_t cursor = begin;
+        const uint32_t n_pending = cb.pend_count[pv.f * N_LAYERS + li];
+        if (n_pending == 0) continue;
+        const bool listed = n_pending <= PEND_CAP;      // phase A's list holds them all (order is irrelevant then)
         // candidates are in raster order, so taking the pending ones chunk by chunk keeps every dependency
         // (always raster-earlier) inside the current or an already finished chunk
         do {
             if (threadIdx.x == 0) { n_list = 0; more = 0; }
             __syncthreads();
-            // gather up to PB_LIST pending candidates starting at cursor, preserving order
             uint32_t next_cursor = end;
+            if (listed) {
+                const uint32_t* src = cb.pend_list + (size_t)(pv.f * N_LAYERS + li) * PEND_CAP;
+                for (uint32_t i = threadIdx.x; i < n_pending; i += PB_THREADS) list[i] = src[i];
+                if (threadIdx.x == 0) n_list = (int)n_pending;
+            } else
+            // gather up to PB_LIST pending candidates starting at cursor, preserving order
             for (uint32_t base = cursor; base < end; base += PB_THREADS) {
                 const uint32_t c = base + threadIdx.x;
                 const bool pend = c < end && (cb.flags[c] & ST_PENDING);
