@@ -8,6 +8,10 @@
 // the reference's precision and association: float where it computes in float, double where a double
 // literal promotes the expression.
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "geom.h"
 
 namespace mfk {
@@ -37,6 +41,88 @@ struct ScoreView {
         const int s00 = at(x, y), s10 = at(x + 1, y), s01 = at(x, y + 1), s11 = at(x + 1, y + 1);
         const float v = rx * ry * s00 + rx1 * ry * s10 + rx * ry1 * s01 + rx1 * ry1 * s11;
         return (float)(unsigned char)v;
+    }
+};
+
+// Unaligned little-endian reads built from aligned 32-bit loads (the maps carry slack past their end, context.cu).
+__device__ __forceinline__ uint32_t load4(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+    return __funnelshift_r(q[0], q[1], (unsigned)(a & 3) * 8);
+#else
+    uint32_t v; memcpy(&v, p, 4); return v;
+#endif
+}
+// bytes p[0..7] as two little-endian words
+__device__ __forceinline__ void load8(const uint8_t* p, uint32_t& lo, uint32_t& hi) {
+#ifdef __CUDA_ARCH__
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+    const uint32_t q0 = q[0], q1 = q[1], q2 = q[2];
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    lo = __funnelshift_r(q0, q1, sh);
+    hi = __funnelshift_r(q1, q2, sh);
+#else
+    memcpy(&lo, p, 4); memcpy(&hi, p + 4, 4);
+#endif
+}
+// bytes p[0..3] in `first4`, p[4] returned
+__device__ __forceinline__ uint32_t load5(const uint8_t* p, uint32_t& first4) {
+#ifdef __CUDA_ARCH__
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+    const uint32_t lo = q[0], hi = q[1];
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    first4 = __funnelshift_r(lo, hi, sh);
+    return (hi >> sh) & 0xffu;
+#else
+    memcpy(&first4, p, 4); return p[4];
+#endif
+}
+
+// A 4x4 window of a neighbouring layer's score map held in registers.  The footprint of a getScoreMaxAbove /
+// getScoreMaxBelow scan, including the 3x3 refinement around its integer maximum and the tie-break reads of
+// the below scan, stays inside 4 x 4 cells: footprint widths are 4/6, 6/8, 8/6 and 6/4 of a cell, so per axis the
+// walk reads [int(a_1), int(a1)+1] when the footprint crosses an integer and [int(a_1)-1, int(a_1)+2] when it does
+// not (then the integer maximum can sit on either side, brisk.cpp:1139-1157); window_origin() picks the start.  Loading it once with 8 aligned loads replaces the
+// ~50 dependent byte loads of the cell-by-cell walk; `touched` records which cells the walk read, i.e. the
+// write-back side effect of the reference's lazy getAgastScore.
+struct Window4 {
+    uint32_t row[4];
+    int x0, y0, w, h;
+    uint32_t touched;
+
+    __device__ __forceinline__ void load(const uint8_t* S, int w_, int h_, int x0_, int y0_) {
+        w = w_; h = h_; x0 = x0_; y0 = y0_; touched = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) row[r] = load4(S + (y0 + r) * w + x0);
+    }
+    __device__ __forceinline__ int at(int x, int y) {
+        if (x < 3 || y < 3 || x >= w - 3 || y >= h - 3) return 0;
+        const int r = y - y0, c = x - x0;
+#ifndef __CUDA_ARCH__
+        if (r < 0 || r > 3 || c < 0 || c > 3) { fprintf(stderr, "Window4 violated: x=%d y=%d x0=%d y0=%d w=%d h=%d\n", x, y, x0, y0, w, h); abort(); }   // the CPU harness checks the 4x4 claim on every read
+#endif
+        touched |= 1u << (r * 4 + c);
+        const uint32_t v = r == 0 ? row[0] : (r == 1 ? row[1] : (r == 2 ? row[2] : row[3]));
+        return (int)((v >> (8 * c)) & 0xffu);
+    }
+    __device__ __forceinline__ float atf(float xf, float yf) {
+        const int x = int(xf);
+        const float rx1 = xf - float(x);
+        const float rx = 1.0f - rx1;
+        const int y = int(yf);
+        const float ry1 = yf - float(y);
+        const float ry = 1.0f - ry1;
+        const int s00 = at(x, y), s10 = at(x + 1, y), s01 = at(x, y + 1), s11 = at(x + 1, y + 1);
+        const float v = rx * ry * s00 + rx1 * ry * s10 + rx * ry1 * s01 + rx1 * ry1 * s11;
+        return (float)(unsigned char)v;
+    }
+    __device__ __forceinline__ void flush_marks(uint8_t* seen) const {
+#pragma unroll
+        for (int b = 0; b < 16; b++)
+            if (touched & (1u << b)) seen[(y0 + (b >> 2)) * w + x0 + (b & 3)] = 1;
     }
 };
 
@@ -144,11 +230,13 @@ __device__ inline float refine1D_fit(const int kind, const float s_05, const flo
 
 struct Scan { bool ismax; float max, dx, dy; };
 
-// getScoreMaxAbove (below == false) / getScoreMaxBelow (below == true) of candidate (x_layer, y_layer)
-// on layer `layer` over the neighbouring layer N.
-__device__ inline Scan scan_neighbour(const ScoreView N, const bool below, const int layer, const int x_layer,
-                                      const int y_layer, const int threshold) {
-    Scan R; R.ismax = false; R.max = 0.0f; R.dx = 0.0f; R.dy = 0.0f;
+// Sampling footprint in the neighbouring layer: getScoreMaxAbove (below == false, brisk.cpp:1122-1135) /
+// getScoreMaxBelow (below == true, :1263-1275) of candidate (x_layer, y_layer) on layer `layer`.
+struct Footprint { float x_1, x1, y_1, y1; };
+
+__device__ __forceinline__ int window_origin(float a_1, float a1) { return int(a1) > int(a_1) ? int(a_1) : int(a_1) - 1; }
+
+__device__ __forceinline__ Footprint scan_footprint(const bool below, const int layer, const int x_layer, const int y_layer) {
     float x_1, x1, y_1, y1;
     if (!below) {
         if (layer % 2 == 0) {
@@ -167,6 +255,15 @@ __device__ inline Scan scan_neighbour(const ScoreView N, const bool below, const
             y_1 = (float)((double)float(6 * y_layer + 1 - 3) / 4.0); y1 = (float)((double)float(6 * y_layer + 1 + 3) / 4.0);
         }
     }
+    Footprint f; f.x_1 = x_1; f.x1 = x1; f.y_1 = y_1; f.y1 = y1;
+    return f;
+}
+
+// The scan itself over a loaded window: getScoreMaxAbove (:1138-1249) / getScoreMaxBelow (:1281-1416).
+__device__ inline Scan scan_neighbour(Window4& N, const Footprint fp, const bool below, const int layer, const int x_layer,
+                                      const int y_layer, const int threshold) {
+    Scan R; R.ismax = false; R.max = 0.0f; R.dx = 0.0f; R.dy = 0.0f;
+    const float x_1 = fp.x_1, x1 = fp.x1, y_1 = fp.y_1, y1 = fp.y1;
     const int xa = int(x_1 + 1), xb = int(x1);
     const int ya = int(y_1 + 1), yb = int(y1);
     int max_x = xa, max_y = ya;
@@ -252,30 +349,44 @@ __device__ inline Scan scan_neighbour(const ScoreView N, const bool below, const
     return R;
 }
 
-// AGAST-5/8 closed-form score with b0 = 0 (agast5_8_nms.cc:42; ring offsets agast5_8.h:65-75), 2-px border
-// (BriskLayer::getAgastScore_5_8, brisk.cpp:1702-1709).  Same packed scheme as the 9/16 score: every ring
-// pixel is the pair (v, 255 - v) in one word, so one 3-input packed minimum serves the brighter and the darker
-// test at once.  (A scalar max(best, max(mn, -mx)) formulation is miscompiled by nvcc 12.9 for sm_100a: ptxas
-// folds the negation into a VIMNMX3 operand and drops it; see DESIGN.md "toolchain notes".)
-__device__ inline int agast58_score(const uint8_t* img, int w, int h, int x, int y) {
-    if (x < 2 || y < 2 || x >= w - 2 || y >= h - 2) return 0;
-    const uint8_t* p = img + y * w + x;
-    const int c = *p;
-    const int ofs[8] = {-1, -w - 1, -w, -w + 1, 1, w + 1, w, w - 1};
-    uint32_t r[8];
+// AGAST-5/8 closed-form scores with b0 = 0 (agast5_8_nms.cc:42; ring offsets agast5_8.h:65-75) at the nine positions
+// (x+dx, y+dy), dx, dy in -1..1, out[(dy+1)*3 + (dx+1)] — what refine3D reads on layer 0 through
+// BriskLayer::getAgastScore_5_8 (brisk.cpp:959-986, 1702-1709).  The 5x5 image window is loaded once (10 aligned
+// loads) and every pixel is packed as (v, 255 - v), so one 3-input packed minimum serves the brighter and the
+// darker test at once, as in the 9/16 score.  Requires 3 <= x < w-3, 3 <= y < h-3 (true for every candidate), which
+// also keeps all nine positions inside getAgastScore_5_8's 2-px border.
+// (A scalar max(best, max(mn, -mx)) formulation is miscompiled by nvcc 12.9 for sm_100a: ptxas folds the negation
+// into a VIMNMX3 operand and drops it; see DESIGN.md "toolchain notes" and tests/repro/.)
+__device__ inline void agast58_patch9(const uint8_t* img, int w, int x, int y, int out[9]) {
+    uint32_t X[5][5];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { const uint32_t v = p[ofs[i]]; r[i] = v | ((255u - v) << 16); }
-    uint32_t best = 0;
+    for (int r = 0; r < 5; r++) {
+        uint32_t first4;
+        const uint32_t fifth = load5(img + (y - 2 + r) * w + (x - 2), first4);
 #pragma unroll
-    for (int s = 0; s < 8; s++) {
-        uint32_t m = __vimin3_u16x2(r[s], r[(s + 1) & 7], r[(s + 2) & 7]);
-        m = __vimin3_u16x2(m, r[(s + 3) & 7], r[(s + 4) & 7]);
-        best = __vimax3_u16x2(best, m, m);
+        for (int c = 0; c < 4; c++) { const uint32_t v = (first4 >> (8 * c)) & 0xffu; X[r][c] = v | ((255u - v) << 16); }
+        X[r][4] = fifth | ((255u - fifth) << 16);
     }
-    const int brighter = (int)(best & 0xffffu) - c;
-    const int darker = (int)(best >> 16) - (255 - c);
-    const int s = (brighter > darker ? brighter : darker) - 1;
-    return s < 0 ? 0 : (s > 254 ? 254 : s);
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 3; dx++) {
+            const int cy = dy + 1, cx = dx + 1;
+            const uint32_t r[8] = {X[cy][cx - 1], X[cy - 1][cx - 1], X[cy - 1][cx], X[cy - 1][cx + 1],
+                                   X[cy][cx + 1], X[cy + 1][cx + 1], X[cy + 1][cx], X[cy + 1][cx - 1]};
+            uint32_t best = 0;
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                uint32_t m = __vimin3_u16x2(r[s], r[(s + 1) & 7], r[(s + 2) & 7]);
+                m = __vimin3_u16x2(m, r[(s + 3) & 7], r[(s + 4) & 7]);
+                best = __vimax3_u16x2(best, m, m);
+            }
+            const int c = (int)(X[cy][cx] & 0xffffu);
+            const int brighter = (int)(best & 0xffffu) - c;
+            const int darker = (int)(best >> 16) - (255 - c);
+            const int sc = (brighter > darker ? brighter : darker) - 1;
+            out[dy * 3 + dx] = sc < 0 ? 0 : (sc > 254 ? 254 : sc);
+        }
 }
 
 }  // namespace mfk

@@ -290,10 +290,12 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     c->row_cap = F * c->row_cap_pair * 4;       // several batches may accumulate before a fetch
     const size_t px = (size_t)width * height;
     CUC(dalloc(&c->store, (size_t)store_frames * px + 64));
-    CUC(dalloc(&c->maps.img, F * c->pyr_px + 64));
-    CUC(dalloc(&c->maps.S, F * c->pyr_px + 64));
-    CUC(dalloc(&c->maps.seen, F * c->pyr_px + 64));
-    CUC(dalloc(&c->maps.status, F * c->pyr_px + 64));
+    // slack: register windows (brisk_device.cuh Window4 / load5) read up to 4 rows + 8 bytes past a layer's end
+    const size_t slack = (size_t)4 * width + 64;
+    CUC(dalloc(&c->maps.img, F * c->pyr_px + slack));
+    CUC(dalloc(&c->maps.S, F * c->pyr_px + slack));
+    CUC(dalloc(&c->maps.seen, F * c->pyr_px + slack));
+    CUC(dalloc(&c->maps.status, F * c->pyr_px + slack));
     CUC(dalloc(&c->integral, F * (size_t)(width + 1) * (height + 1)));
     CUC(dalloc(&c->cb.row_count, F * c->rows + 2));
     CUC(dalloc(&c->cb.xy, cand_cap)); CUC(dalloc(&c->cb.meta, cand_cap));

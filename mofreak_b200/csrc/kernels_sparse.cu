@@ -19,33 +19,59 @@ namespace mfk {
 // ---------------------------------------------------------------------------------------------------
 // phase A
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_phase_a(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
+// Two steps per chunk of PA_CHUNK candidates, so that the expensive part runs on full warps:
+//   1. every thread tests PA_ITEMS candidates against their 8 neighbours (3 aligned row loads each); losers are
+//      final, candidates with an equal neighbour go to the pair's tie list, the rest to a shared-memory queue;
+//   2. the block drains the queue, one thread per surviving candidate (scans, refinement, keypoint record).
+constexpr int PA_THREADS = 128, PA_ITEMS = 8, PA_CHUNK = PA_THREADS * PA_ITEMS;
+
+__global__ void __launch_bounds__(PA_THREADS) k_phase_a(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
+    __shared__ uint32_t queue[PA_CHUNK];
+    __shared__ int q_n;
     const uint32_t n = min(cb.row_count[g.F * g.rows], (uint32_t)g.cand_cap);
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-        const uint32_t xy = cb.xy[c], meta = cb.meta[c];
-        const int x = xy & 0xffff, y = xy >> 16, li = meta & 7;
-        PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
-        const LayerGeom& L = g.L[li];
-        const uint8_t* S = m.S + pv.off(li) + y * L.w + x;
-        // isMax2D, order-independent part (brisk.cpp:838-869): neighbours below the threshold can never exceed
-        // or equal a candidate, so the dense map can be read directly
-        const int c0 = S[0];
-        const int n0 = S[-L.w - 1], n1 = S[-L.w], n2 = S[-L.w + 1], n3 = S[-1], n4 = S[1], n5 = S[L.w - 1], n6 = S[L.w], n7 = S[L.w + 1];
-        const int mx = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
-        uint8_t* status = m.status + pv.off(li) + y * L.w + x;
-        if (mx > c0) { *status = 0; cb.flags[c] = 0; continue; }
-        if (mx == c0) {
-            *status = ST_PENDING; cb.flags[c] = ST_PENDING;
-            const uint32_t slot = atomicAdd(&cb.pend_count[pv.f * N_LAYERS + li], 1u);
-            if (slot < PEND_CAP) cb.pend_list[(size_t)(pv.f * N_LAYERS + li) * PEND_CAP + slot] = c;
-            continue;
+    for (uint32_t base = blockIdx.x * PA_CHUNK; base < n; base += gridDim.x * PA_CHUNK) {
+        if (threadIdx.x == 0) q_n = 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PA_ITEMS; k++) {
+            const uint32_t c = base + k * PA_THREADS + threadIdx.x;
+            if (c >= n) continue;
+            const uint32_t xy = cb.xy[c], meta = cb.meta[c];
+            const int x = xy & 0xffff, y = xy >> 16, li = meta & 7, f = meta >> 3;
+            const LayerGeom& L = g.L[li];
+            const size_t off = L.base + (size_t)f * L.px;
+            const uint8_t* S = m.S + off + y * L.w + x;
+            // isMax2D, order-independent part (brisk.cpp:838-869): neighbours below the threshold can never exceed
+            // or equal a candidate, so the dense map can be read directly
+            const uint32_t r0 = load4(S - L.w - 1), r1 = load4(S - 1), r2 = load4(S + L.w - 1);
+            const int c0 = (r1 >> 8) & 0xff;
+            const uint32_t m01 = __vmaxu4(r0 & 0xffffffu, r2 & 0xffffffu);          // rows above and below, 3 cells each
+            const uint32_t m02 = __vmaxu4(m01, r1 & 0xff00ffu);                      // left and right neighbour
+            const int mx = max(max((int)(m02 & 0xff), (int)((m02 >> 8) & 0xff)), (int)((m02 >> 16) & 0xff));
+            uint8_t* status = m.status + off + y * L.w + x;
+            if (mx > c0) { *status = 0; cb.flags[c] = 0; continue; }
+            if (mx == c0) {
+                *status = ST_PENDING; cb.flags[c] = ST_PENDING;
+                const uint32_t slot = atomicAdd(&cb.pend_count[f * N_LAYERS + li], 1u);
+                if (slot < PEND_CAP) cb.pend_list[(size_t)(f * N_LAYERS + li) * PEND_CAP + slot] = c;
+                continue;
+            }
+            queue[atomicAdd(&q_n, 1)] = c;
         }
-        after_max2d(pv, cb, tb, li, x, y, c);
+        __syncthreads();
+        const int qn = q_n;
+        for (int i = threadIdx.x; i < qn; i += PA_THREADS) {
+            const uint32_t c = queue[i];
+            const uint32_t xy = cb.xy[c], meta = cb.meta[c];
+            PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
+            after_max2d(pv, cb, tb, meta & 7, xy & 0xffff, xy >> 16, c);
+        }
+        __syncthreads();
     }
 }
 
 void launch_phase_a(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTables tb) {
-    k_phase_a<<<148 * 8, 128, 0, st>>>(g, m, cb, tb);
+    k_phase_a<<<148 * 8, PA_THREADS, 0, st>>>(g, m, cb, tb);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -112,8 +138,10 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
                     if (c == 0xffffffffu) continue;
                     const uint32_t xy = cb.xy[c];
                     const int x = xy & 0xffff, y = xy >> 16;
-                    if (earlier_pending_nearby(pv, li, x, y)) continue;
-                    verdict[i] = tie_break(pv, li, x, y) ? 2 : 1;
+                    TieWindow tw;
+                    tw.load(pv, li, x, y);
+                    if (earlier_pending_nearby(tw)) continue;
+                    verdict[i] = tie_break(tw) ? 2 : 1;
                 }
                 __syncthreads();
                 for (int i = threadIdx.x; i < nl; i += PB_THREADS) {

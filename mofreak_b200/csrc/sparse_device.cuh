@@ -31,35 +31,51 @@ __device__ __forceinline__ int freak_scale_index(const float* __restrict__ thr, 
 
 // Everything after a successful isMax2D for candidate c = (x, y) on layer li: the scans, and for survivors the
 // refined keypoint.  Writes the candidate's final status byte and, for keypoints, its record.
+// All global reads are issued up front: the 3x3 own-layer patch, a 4x4 window of the layer above and of the layer
+// below (Window4) and, on layer 0, the 5x5 image window of the AGAST-5/8 stand-in scores.
 __device__ inline void after_max2d(const PairView& pv, const CandBuf& cb, const DeviceTables& tb, int li, int x, int y, uint32_t c) {
     const Geom& g = *pv.g;
     const LayerGeom& L = g.L[li];
-    const ScoreView own = pv.scores(li, false);
+    const uint8_t* Sown = pv.m.S + pv.off(li);
     uint8_t* status = pv.m.status + pv.off(li) + y * L.w + x;
-    const int center = own.S[y * L.w + x];
     uint8_t st = ST_PASS2D;
+
+    // own-layer 3x3 patch (the dense map already holds 0 inside the 3-px border, as getAgastScore returns there)
+    const uint32_t p0 = load4(Sown + (y - 1) * L.w + x - 1), p1 = load4(Sown + y * L.w + x - 1), p2 = load4(Sown + (y + 1) * L.w + x - 1);
+    const bool has_above = li < N_LAYERS - 1, has_below = li > 0;
+    Window4 wa, wb;
+    Footprint fa, fb;
+    if (has_above) {
+        fa = scan_footprint(false, li, x, y);
+        wa.load(pv.m.S + pv.off(li + 1), g.L[li + 1].w, g.L[li + 1].h, window_origin(fa.x_1, fa.x1), window_origin(fa.y_1, fa.y1));
+    }
+    if (has_below) {
+        fb = scan_footprint(true, li, x, y);
+        wb.load(pv.m.S + pv.off(li - 1), g.L[li - 1].w, g.L[li - 1].h, window_origin(fb.x_1, fb.x1), window_origin(fb.y_1, fb.y1));
+    }
+    int a58[9];
+    if (li == 0) agast58_patch9(pv.m.img + pv.off(0), L.w, x, y, a58);
+
+    const int s_0_0 = p0 & 0xff, s_1_0 = (p0 >> 8) & 0xff, s_2_0 = (p0 >> 16) & 0xff;
+    const int s_0_1 = p1 & 0xff, s_1_1 = (p1 >> 8) & 0xff, s_2_1 = (p1 >> 16) & 0xff;
+    const int s_0_2 = p2 & 0xff, s_1_2 = (p2 >> 8) & 0xff, s_2_2 = (p2 >> 16) & 0xff;
+    const int center = s_1_1;
 
     Scan up, dn;
     up.ismax = true; up.max = 0.f; up.dx = 0.f; up.dy = 0.f;
     dn = up;
-    if (li < N_LAYERS - 1) {
-        up = scan_neighbour(pv.scores(li + 1, true), false, li, x, y, center);      // marks layer li+1
+    if (has_above) {
+        up = scan_neighbour(wa, fa, false, li, x, y, center);
+        wa.flush_marks(pv.m.seen + pv.off(li + 1));             // getScoreMaxAbove's write-backs, even on early exit
         if (!up.ismax) { *status = st; cb.flags[c] = st; return; }
-        if (li > 0) {
-            dn = scan_neighbour(pv.scores(li - 1, false), true, li, x, y, center);
-            if (!dn.ismax) { *status = st; cb.flags[c] = st; return; }
-        }
-    } else {
-        dn = scan_neighbour(pv.scores(li - 1, false), true, li, x, y, center);
+    }
+    if (has_below) {
+        dn = scan_neighbour(wb, fb, true, li, x, y, center);
         if (!dn.ismax) { *status = st; cb.flags[c] = st; return; }
     }
     st |= ST_SURVIVE;
     *status = st;       // from here on the candidate's own 3x3 patch counts as touched
 
-    // own-layer patch
-    const int s_0_0 = own.at(x - 1, y - 1), s_1_0 = own.at(x, y - 1), s_2_0 = own.at(x + 1, y - 1);
-    const int s_2_1 = own.at(x + 1, y), s_1_1 = own.at(x, y), s_0_1 = own.at(x - 1, y);
-    const int s_0_2 = own.at(x - 1, y + 1), s_1_2 = own.at(x, y + 1), s_2_2 = own.at(x + 1, y + 1);
     float delta_x_layer, delta_y_layer;
     const float max_layer = subpixel2D(s_0_0, s_0_1, s_0_2, s_1_0, s_1_1, s_1_2, s_2_0, s_2_1, s_2_2, delta_x_layer, delta_y_layer);
 
@@ -75,12 +91,8 @@ __device__ inline void after_max2d(const PairView& pv, const CandBuf& cb, const 
         float max_below = dn.max, delta_x_below = dn.dx, delta_y_below = dn.dy;
         if (li == 0) {
             // no layer below layer 0: 5/8 scores on the same image stand in (brisk.cpp:959-986)
-            const uint8_t* img0 = pv.m.img + pv.off(0);
-            const int a_0_0 = agast58_score(img0, L.w, L.h, x - 1, y - 1), a_1_0 = agast58_score(img0, L.w, L.h, x, y - 1);
-            const int a_2_0 = agast58_score(img0, L.w, L.h, x + 1, y - 1), a_2_1 = agast58_score(img0, L.w, L.h, x + 1, y);
-            const int a_1_1 = agast58_score(img0, L.w, L.h, x, y), a_0_1 = agast58_score(img0, L.w, L.h, x - 1, y);
-            const int a_0_2 = agast58_score(img0, L.w, L.h, x - 1, y + 1), a_1_2 = agast58_score(img0, L.w, L.h, x, y + 1);
-            const int a_2_2 = agast58_score(img0, L.w, L.h, x + 1, y + 1);
+            const int a_0_0 = a58[0], a_1_0 = a58[1], a_2_0 = a58[2], a_0_1 = a58[3], a_1_1 = a58[4], a_2_1 = a58[5];
+            const int a_0_2 = a58[6], a_1_2 = a58[7], a_2_2 = a58[8];
             const int m = max(max(max(a_0_0, a_1_0), max(a_2_0, a_2_1)), max(max(a_1_1, a_0_1), max(max(a_0_2, a_1_2), a_2_2)));
             subpixel2D(a_0_0, a_0_1, a_0_2, a_1_0, a_1_1, a_1_2, a_2_0, a_2_1, a_2_2, delta_x_below, delta_y_below);
             max_below = (float)m;
@@ -138,67 +150,81 @@ __device__ inline void after_max2d(const PairView& pv, const CandBuf& cb, const 
     cb.flags[c] = st;
 }
 
-// what the reference's raw score map holds at q = (qx, qy) when candidate index cidx of this layer runs isMax2D
-__device__ __forceinline__ int raw_at(const ScoreView& own, const uint8_t* __restrict__ seen, const uint8_t* __restrict__ status,
-                                      int qx, int qy, int cidx) {
-    const int s = own.at(qx, qy);
-    if (s == 0 || s >= BRISK_THRESHOLD) return s;
-    if (seen[qy * own.w + qx]) return s;
-    for (int dy = -1; dy <= 1; dy++)
-        for (int dx = -1; dx <= 1; dx++) {
-            const int nx = qx + dx, ny = qy + dy;
-            const int nidx = ny * own.w + nx;
-            if (nidx >= cidx) continue;
-            if (own.at(nx, ny) < BRISK_THRESHOLD) continue;
-            if (status[nidx] & ST_SURVIVE) return s;
+// ---- tie candidates (phase B) ----------------------------------------------------------------------------------
+// Everything a tie candidate at (x, y) needs lies within 3 px: the scores and candidate statuses of the 7x7
+// neighbourhood and the "seen" marks of the 5x5.  They are fetched as packed rows with independent aligned loads
+// (x in [3, w-4], y in [3, h-4], so the 7x7 is inside the layer) and all decisions are taken from registers.
+struct TieWindow {
+    uint32_t S[7][2], st[7][2], seen[5][2];
+
+    __device__ __forceinline__ void load(const PairView& pv, int li, int x, int y) {
+        const int w = pv.g->L[li].w;
+        const size_t off = pv.off(li);
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            load8(pv.m.S + off + (y - 3 + r) * w + x - 3, S[r][0], S[r][1]);
+            load8(pv.m.status + off + (y - 3 + r) * w + x - 3, st[r][0], st[r][1]);
         }
-    return 0;
+#pragma unroll
+        for (int r = 0; r < 5; r++) load8(pv.m.seen + off + (y - 2 + r) * w + x - 2, seen[r][0], seen[r][1]);
+    }
+};
+
+__device__ __forceinline__ int packed_byte(const uint32_t r[2], int b) { return (int)((r[b >> 2] >> (8 * (b & 3))) & 0xffu); }
+
+// true while a raster-earlier tie candidate within 3 px is still undecided (status bytes are only defined on
+// candidates, i.e. where S >= threshold)
+__device__ inline bool earlier_pending_nearby(const TieWindow& W) {
+    bool pending = false;
+#pragma unroll
+    for (int r = 0; r <= 3; r++)
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+            if (r == 3 && c >= 3) continue;
+            pending |= packed_byte(W.S[r], c) >= BRISK_THRESHOLD && (packed_byte(W.st[r], c) & ST_PENDING);
+        }
+    return pending;
+}
+
+// what the reference's raw score map holds at window cell (r, c) (7x7 coordinates, candidate at (3, 3)) when the
+// candidate runs isMax2D: the score if it was written by getAgastPoints (>= threshold), or read by a
+// getScoreMaxAbove scan from the layer below, or lies in the 3x3 patch of a raster-earlier survivor; else 0
+__device__ __forceinline__ int raw_cell(const TieWindow& W, const int r, const int c) {
+    const int s = packed_byte(W.S[r], c);
+    if (s == 0 || s >= BRISK_THRESHOLD) return s;
+    if (packed_byte(W.seen[r - 1], c - 1)) return s;
+    bool touched = false;
+#pragma unroll
+    for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+        for (int dc = -1; dc <= 1; dc++) {
+            const int a = r + dr, b = c + dc;
+            if (a > 3 || (a == 3 && b >= 3)) continue;                       // not raster-earlier than the candidate
+            touched |= packed_byte(W.S[a], b) >= BRISK_THRESHOLD && (packed_byte(W.st[a], b) & ST_SURVIVE);
+        }
+    return touched ? s : 0;
 }
 
 // the smoothed tie-break of isMax2D, brisk.cpp:870-933
-__device__ inline bool tie_break(const PairView& pv, int li, int x, int y) {
-    const LayerGeom& L = pv.g->L[li];
-    const ScoreView own = pv.scores(li, false);
-    const uint8_t* seen = pv.m.seen + pv.off(li);
-    const uint8_t* status = pv.m.status + pv.off(li);
-    const int cidx = y * L.w + x;
+__device__ inline bool tie_break(const TieWindow& W) {
     int r[5][5];
 #pragma unroll
-    for (int dy = -2; dy <= 2; dy++)
+    for (int i = 0; i < 5; i++)
 #pragma unroll
-        for (int dx = -2; dx <= 2; dx++) r[dy + 2][dx + 2] = raw_at(own, seen, status, x + dx, y + dy, cidx);
+        for (int j = 0; j < 5; j++) r[i][j] = raw_cell(W, i + 1, j + 1);
     const int center = r[2][2];
-    auto smooth = [&](int cx, int cy) {
-        return 4 * r[cy][cx] + 2 * (r[cy][cx - 1] + r[cy][cx + 1] + r[cy - 1][cx] + r[cy + 1][cx]) + r[cy - 1][cx - 1] +
-               r[cy - 1][cx + 1] + r[cy + 1][cx - 1] + r[cy + 1][cx + 1];
-    };
-    const int mine = smooth(2, 2);
     bool ok = true;
+    int mine = 0;
 #pragma unroll
-    for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-        for (int dx = -1; dx <= 1; dx++) {
-            if (!dx && !dy) continue;
-            if (r[dy + 2][dx + 2] == center && smooth(dx + 2, dy + 2) > mine) ok = false;
-        }
+    for (int k = 0; k < 9; k++) {
+        // k = 0 is the candidate itself, then its eight neighbours
+        const int cy = (k == 0) ? 2 : 1 + ((k - 1 + (k > 4)) / 3), cx = (k == 0) ? 2 : 1 + ((k - 1 + (k > 4)) % 3);
+        const int sm = 4 * r[cy][cx] + 2 * (r[cy][cx - 1] + r[cy][cx + 1] + r[cy - 1][cx] + r[cy + 1][cx]) + r[cy - 1][cx - 1] +
+                       r[cy - 1][cx + 1] + r[cy + 1][cx - 1] + r[cy + 1][cx + 1];
+        if (k == 0) mine = sm;
+        else if (r[cy][cx] == center && sm > mine) ok = false;
+    }
     return ok;
 }
-
-__device__ inline bool earlier_pending_nearby(const PairView& pv, int li, int x, int y) {
-    const LayerGeom& L = pv.g->L[li];
-    const ScoreView own = pv.scores(li, false);
-    const uint8_t* status = pv.m.status + pv.off(li);
-    const int cidx = y * L.w + x;
-    for (int dy = -3; dy <= 0; dy++)
-        for (int dx = -3; dx <= 3; dx++) {
-            const int nx = x + dx, ny = y + dy;
-            const int nidx = ny * L.w + nx;
-            if (nidx >= cidx) continue;
-            if (own.at(nx, ny) < BRISK_THRESHOLD) continue;      // status bytes are only defined on candidates
-            if (status[nidx] & ST_PENDING) return true;
-        }
-    return false;
-}
-
 
 }  // namespace mfk

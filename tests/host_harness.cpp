@@ -58,8 +58,9 @@ struct Harness {
             g.L[l].scale = scale[l]; g.L[l].offset = (float)(0.5 * scale[l] - 0.5);
             below += g.L[l].px; row0 += lh[l];
         }
-        g.W = W; g.H = H; g.F = 1; g.rows = row0; g.pyr_px = (int)below; g.cand_cap = (int)below; g.row_cap = (int)below;
-        img.assign(below, 0); S.assign(below, 0); seen.assign(below, 0); status.assign(below, 0xAA);  // status is NOT zero-initialised on the device either
+        g.W = W; g.H = H; g.F = 1; g.rows = row0; g.pyr_px = (int)below; g.cand_cap = (int)below; g.row_cap = (int)below;   // before slack
+        const size_t alloc = below + 4 * (size_t)W + 64;      // same slack as the device allocations (windows read past the end)
+        img.assign(alloc, 0); S.assign(alloc, 0); seen.assign(alloc, 0); status.assign(alloc, 0xAA);  // status is NOT zero-initialised on the device either
         maps.img = img.data(); maps.S = S.data(); maps.seen = seen.data(); maps.status = status.data();
         const Tables& T = tables();
         tb.points = T.points; tb.pattern_size = T.pattern_size; tb.scale_threshold = T.scale_threshold;
@@ -134,8 +135,10 @@ struct Harness {
                 for (size_t i = 0; i < list.size(); i++) {
                     if (list[i] == 0xffffffffu) continue;
                     const int x = xy[list[i]] & 0xffff, y = xy[list[i]] >> 16;
-                    if (earlier_pending_nearby(pv, li, x, y)) continue;
-                    verdict[i] = tie_break(pv, li, x, y) ? 2 : 1;
+                    TieWindow tw;
+                    tw.load(pv, li, x, y);
+                    if (earlier_pending_nearby(tw)) continue;
+                    verdict[i] = tie_break(tw) ? 2 : 1;
                 }
                 for (size_t i = 0; i < list.size(); i++) {
                     if (!verdict[i]) continue;
