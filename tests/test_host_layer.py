@@ -1,0 +1,159 @@
+"""The C++ host classes that keep the reference's call surface (mofreak_b200/host/): MoFREAKUtilities,
+MotionInterchangePatterns, BagOfWordsRepresentation — driven through their extern "C" shim."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import mofreak_b200
+from tests import util
+
+HOST_DIR = os.path.join(os.path.dirname(mofreak_b200.__file__), "host")
+
+
+@pytest.fixture(scope="module")
+def host():
+    path = os.path.join(HOST_DIR, "libmofreak_host.so")
+    if not os.path.exists(path):
+        mofreak_b200.build.build()
+        subprocess.run(["make", "-s", "-C", HOST_DIR], check=True)
+    L = C.CDLL(path)
+    L.mfkh_compute_mofreak_from_file.restype = C.c_long
+    L.mfkh_rewrite_mofreak.restype = C.c_long
+    return L
+
+
+def clusters_text(cb):
+    return "".join(" ".join(str(int(v)) for v in row) + " \n" for row in cb)
+
+
+def libsvm_line(label, hist):
+    return "%d " % label + "".join("%d:%g " % (i + 1, float(v)) for i, v in enumerate(hist))
+
+
+# ---------------------------------------------------------------------------------------------- CPU side
+def test_reader_writer_round_trip_is_byte_identical(host, tmp_path):
+    name = "kth_160x120x100_seed1"
+    src = tmp_path / "in.mofreak"; dst = tmp_path / "out.mofreak"
+    src.write_text(util.golden_text(name))
+    n = host.mfkh_rewrite_mofreak(str(src).encode(), str(dst).encode())
+    assert n == len(util.golden_rows(name))
+    # %g keeps 6 significant digits, so text -> float -> text is the identity on the reference's own output
+    assert dst.read_text() == util.golden_text(name)
+
+
+def test_load_clusters_quirk_matches_oracle(host, orc, tmp_path):
+    rng = np.random.default_rng(3)
+    cb = rng.integers(0, 256, (9, 16), dtype=np.uint8)
+    (tmp_path / "clusters.txt").write_text(clusters_text(cb))
+    out = np.zeros((16, 16), np.uint8)
+    K = host.mfkh_bow_codebook(9, str(tmp_path).encode(), out.ctypes.data_as(C.c_void_p), 16)
+    want = orc.load_clusters(clusters_text(cb))
+    assert K == len(want) == 9
+    assert np.array_equal(out[:K], want)
+    assert np.array_equal(out[:8], cb[1:]) and (out[8] == cb[8, 15]).all()      # line k+2; last word repeats the last value
+
+
+def test_gray_video_container(host, tmp_path):
+    clip = mofreak_b200.synth_clip(160, 120, 3, 5)
+    p = tmp_path / "clip.y8"
+    assert host.mfkh_write_gray_video(str(p).encode(), clip.ctypes.data_as(C.c_void_p), 160, 120, 3) == 0
+    raw = p.read_bytes()
+    assert raw[:8] == b"MFKGRAY1" and np.frombuffer(raw[8:20], "<i4").tolist() == [160, 120, 3]
+    assert raw[20:] == clip.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------- GPU side
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["kth_160x120x100_seed1", "odd_212x163x9_seed7"])
+def test_compute_mofreak_from_file_writes_the_golden_file(host, tmp_path, name):
+    c = util.golden_cases()[name]
+    clip = mofreak_b200.synth_clip(c["width"], c["height"], c["frames"], c["seed"])
+    video = tmp_path / "person01_boxing_d1_uncomp.y8"; out = tmp_path / "person01_boxing_d1_uncomp.mofreak"
+    host.mfkh_write_gray_video(str(video).encode(), clip.ctypes.data_as(C.c_void_p), c["width"], c["height"], c["frames"])
+    n = host.mfkh_compute_mofreak_from_file(0, str(video).encode(), str(out).encode())
+    assert n == c["rows"]
+    assert out.read_text() == util.golden_text(name)          # the .mofreak file is byte-identical
+
+
+@pytest.mark.gpu
+def test_command_line_driver(tmp_path):
+    exe = os.path.join(HOST_DIR, "mofreak_main")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", HOST_DIR], check=True)
+    c = util.golden_cases()["ucf_320x240x12_seed3"]
+    clip = mofreak_b200.synth_clip(c["width"], c["height"], c["frames"], c["seed"])
+    video = tmp_path / "v_Archery_g01_c01.y8"
+    video.write_bytes(b"MFKGRAY1" + np.array([c["width"], c["height"], c["frames"]], "<i4").tobytes() + clip.tobytes())
+    r = subprocess.run([exe, "detect", "UCF101", str(tmp_path), str(video)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "v_Archery_g01_c01.mofreak").read_text() == util.golden_text("ucf_320x240x12_seed3")
+
+
+@pytest.mark.gpu
+def test_bag_of_words_cross_validation_files(host, orc, tmp_path):
+    rng = np.random.default_rng(5)
+    K, groups = 40, 3
+    cb = rng.integers(0, 256, (K + 1, 16), dtype=np.uint8)         # first line is skipped by the loader
+    cb[-1] = cb[-1, 15]                                            # keep the last (repeated-value) codeword well defined
+    (tmp_path / "clusters.txt").write_text(clusters_text(cb))
+    loaded = orc.load_clusters(clusters_text(cb))
+    names = ["person01_boxing_d1_uncomp.mofreak", "person02_boxing_d2_uncomp.mofreak", "person02_walking_d1_uncomp.mofreak",
+             "person03_running_d4_uncomp.mofreak"]
+    files, expect = [], []
+    actions = {}
+    for i, nm in enumerate(names):
+        clip = mofreak_b200.synth_clip(160, 120, 14, 30 + i)
+        rows = orc.extract_clip(clip)
+        assert len(rows) > 0
+        p = tmp_path / nm
+        p.write_text(orc.format_mofreak(rows))
+        files.append(str(p).encode())
+        ok, hist = orc.build_histogram(orc.format_mofreak(rows), loaded)
+        act = nm.split("_")[1]
+        actions.setdefault(act, len(actions))
+        group = int(nm.split("_")[0][-2:]) - 1
+        expect.append((group, libsvm_line(actions[act] + 1, hist)))
+    arr = (C.c_char_p * len(files))(*files)
+    assert host.mfkh_bow_run(K + 1, str(tmp_path).encode(), groups, 0, arr, len(files)) == K + 1
+    for g in range(groups):
+        train = (tmp_path / ("%d.train" % (g + 1))).read_text().splitlines()
+        test = (tmp_path / ("%d.test" % (g + 1))).read_text().splitlines()
+        assert test == [l for (grp, l) in expect if grp == g]
+        assert train == [l for (grp, l) in expect if grp != g]
+
+
+@pytest.mark.gpu
+def test_sliding_bag_of_words(host, orc, tmp_path):
+    rng = np.random.default_rng(6)
+    cb = rng.integers(0, 256, (21, 16), dtype=np.uint8); cb[-1] = 9
+    (tmp_path / "clusters.txt").write_text(clusters_text(cb))
+    loaded = orc.load_clusters(clusters_text(cb))
+    clip = mofreak_b200.synth_clip(160, 120, 30, 44)
+    rows = orc.extract_clip(clip)
+    mof = tmp_path / "stream.mofreak"; mof.write_text(orc.format_mofreak(rows))
+    alpha = 4
+    outp = tmp_path / "out.txt"
+    host.mfkh_bow_sliding(21, str(tmp_path).encode(), str(mof).encode(), alpha, 7, str(outp).encode())
+    desc = np.concatenate([rows["appearance"], rows["motion"]], 1)
+    idx = orc.bow_assign(desc, loaded)
+    frames = rows["frame"]
+    uniq = sorted(set(frames.tolist()))[:-1]                      # the last frame's rows never form a histogram
+    hists = [np.bincount(idx[frames == f], minlength=21).astype(np.float32) for f in uniq]
+    want = []
+    for i in range(alpha - 1, len(hists)):
+        h = np.sum(hists[i - alpha + 1:i + 1], axis=0, dtype=np.float32)
+        want.append(libsvm_line(7, h / np.float32(h.sum())))
+    assert len(want) > 3
+    assert outp.read_text().splitlines() == want
+
+
+@pytest.mark.gpu
+def test_mip_facade_class(host, orc):
+    clip = mofreak_b200.synth_clip(320, 240, 6, 81)
+    out = np.zeros(8, np.uint8)
+    host.mfkh_mip(clip[5].ctypes.data_as(C.c_void_p), clip[0].ctypes.data_as(C.c_void_p), 320, 240, C.c_float(17.3), 150, 100,
+                  out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, orc.mip_extract(clip[5], clip[0], 17.3, 150, 100))
