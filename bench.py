@@ -226,10 +226,19 @@ def run_ours(args):
     ctx.profile_enable(False)
 
     # ---- end to end: host buffers in, host rows out, copies inside the timed region ----
+    # chunks of whole streams: the upload of chunk k+1 (copy stream) overlaps the kernels of chunk k
+    chunk_streams = max(1, min(STREAMS, MAX_PAIRS // PAIRS_PER_STREAM))
+    chunks = []
+    for s0 in range(0, STREAMS, chunk_streams):
+        s1 = min(STREAMS, s0 + chunk_streams)
+        chunks.append((s0 * FRAMES_PER_STREAM, (s1 - s0) * FRAMES_PER_STREAM, slice(s0 * PAIRS_PER_STREAM, s1 * PAIRS_PER_STREAM)))
+    frame_bytes = W * H
+
     def step_e2e():
         ctx.reset_rows()
-        ctx.upload_raw(host.data_ptr(), n_frames, 0)
-        ctx.extract_pairs(cur, prev, label)
+        for f0, nf, ps in chunks:
+            ctx.upload_raw(host.data_ptr() + f0 * frame_bytes, nf, f0)
+            ctx.extract_pairs(cur[ps], prev[ps], label[ps])
         return ctx.fetch_rows_raw(rows_host.data_ptr(), row_cap)
 
     for _ in range(max(1, args.warmup // 2)):

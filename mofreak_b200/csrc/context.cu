@@ -40,7 +40,13 @@ struct ProfSpan { int id; cudaEvent_t a, b; };
 struct mfk_ctx {
     int device = 0, W = 0, H = 0, store_frames = 0, max_pairs = 0;
     int cand_cap_pair = 0, row_cap_pair = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // all kernels, row fetches
+    cudaStream_t copy_stream = nullptr;   // frame-ring uploads, so that H2D of the next frames overlaps the kernels of these
+    cudaEvent_t upload_done = nullptr;
+    bool upload_pending = false;
+    struct ReadRec { int lo = 0, hi = -1; cudaEvent_t ev = nullptr; bool valid = false; };
+    ReadRec readers[8];                   // which slot ranges recent launch sequences still read
+    int reader_next = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     // geometry template (F filled per batch)
     int lw[N_LAYERS], lh[N_LAYERS], rows = 0, pyr_px = 0;
@@ -213,6 +219,7 @@ void destroy(mfk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     drain_spans(c);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->store); cudaFree(c->maps.img); cudaFree(c->maps.S); cudaFree(c->maps.seen); cudaFree(c->maps.status);
@@ -224,6 +231,9 @@ void destroy(mfk_ctx* c) {
     cudaFree(c->codebook); cudaFree(c->bow_counts); cudaFree(c->bow_tmp);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
+    if (c->upload_done) cudaEventDestroy(c->upload_done);
+    for (auto& r : c->readers) if (r.ev) cudaEventDestroy(r.ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -275,6 +285,9 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     } while (0)
     CUC(cudaSetDevice(device));
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming));
+    for (auto& r : c->readers) CUC(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
     CUC(cudaEventCreate(&c->t0));
     CUC(cudaEventCreate(&c->t1));
     // pyramid geometry, brisk.cpp:1660, 1666
@@ -323,6 +336,7 @@ const char* mfk_last_error(const mfk_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int mfk_sync(mfk_ctx* c) {
     if (!c) return MFK_ERR_ARG;
+    CU(c, cudaStreamSynchronize(c->copy_stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return MFK_OK;
 }
@@ -337,14 +351,19 @@ int mfk_upload_frames(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_fram
     while (done < n_frames) {
         const int slot = (slot0 + done) % c->store_frames;
         const int run = std::min(n_frames - done, c->store_frames - slot);     // contiguous slots before the wrap
+        // slots still being read by queued launch sequences must not be overwritten under them
+        for (auto& r : c->readers)
+            if (r.valid && r.lo <= slot + run - 1 && r.hi >= slot) CU(c, cudaStreamWaitEvent(c->copy_stream, r.ev, 0));
         const uint8_t* src = gray + (size_t)done * stride * c->H;
         if (stride == (size_t)c->W)
-            CU(c, cudaMemcpyAsync(c->store + (size_t)slot * px, src, (size_t)run * px, cudaMemcpyHostToDevice, c->stream));
+            CU(c, cudaMemcpyAsync(c->store + (size_t)slot * px, src, (size_t)run * px, cudaMemcpyHostToDevice, c->copy_stream));
         else
             CU(c, cudaMemcpy2DAsync(c->store + (size_t)slot * px, c->W, src, stride, c->W, (size_t)run * c->H,
-                                    cudaMemcpyHostToDevice, c->stream));
+                                    cudaMemcpyHostToDevice, c->copy_stream));
         done += run;
     }
+    CU(c, cudaEventRecord(c->upload_done, c->copy_stream));
+    c->upload_pending = true;
     return MFK_OK;
 }
 
@@ -362,6 +381,7 @@ int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_s
     int rc = grow_pair_arrays(c, c->pairs_queued + (size_t)n_pairs);
     if (rc != MFK_OK) return rc;
     const size_t first = c->pairs_queued;
+    if (c->upload_pending) { CU(c, cudaStreamWaitEvent(c->stream, c->upload_done, 0)); c->upload_pending = false; }
     CU(c, cudaMemcpyAsync(c->d_cur + first, cur_slot, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->d_prev + first, prev_slot, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->d_label + first, label, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
@@ -371,6 +391,17 @@ int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_s
         if (rc != MFK_OK) return rc;
     }
     c->pairs_queued += (size_t)n_pairs;
+    // remember which slots this call reads until its kernels have run (conservative [min, max] range)
+    int lo = c->store_frames, hi = -1;
+    for (int i = 0; i < n_pairs; i++) {
+        const int a = cur_slot[i] % c->store_frames, b = prev_slot[i] % c->store_frames;
+        lo = std::min(lo, std::min(a, b)); hi = std::max(hi, std::max(a, b));
+    }
+    mfk_ctx::ReadRec& rec = c->readers[c->reader_next];
+    c->reader_next = (c->reader_next + 1) % 8;
+    if (rec.valid) CU(c, cudaStreamWaitEvent(c->copy_stream, rec.ev, 0));       // recycled record: keep its ordering
+    rec.lo = lo; rec.hi = hi; rec.valid = true;
+    CU(c, cudaEventRecord(rec.ev, c->stream));
     return MFK_OK;
 }
 
@@ -462,6 +493,7 @@ int mfk_mip_describe(mfk_ctx* c, int cur_slot, int prev_slot, const float* kp_xy
     float* d_kp = (float*)c->bow_tmp;
     uint8_t* d_mot = (uint8_t*)c->bow_tmp + (size_t)n * 12;
     uint32_t* d_err = (uint32_t*)((uint8_t*)c->bow_tmp + err_off);
+    if (c->upload_pending) { CU(c, cudaStreamWaitEvent(c->stream, c->upload_done, 0)); c->upload_pending = false; }
     CU(c, cudaMemcpyAsync(d_kp, kp_xys, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemsetAsync(d_err, 0, 4, c->stream));
     const size_t px = (size_t)c->W * c->H;
