@@ -9,6 +9,7 @@
 //
 // All of this is byte/integer work bound by memory and integer-issue throughput; no stage is a dense
 // contraction, so tensor cores are not involved.
+#include "brisk_device.cuh"
 #include "dense_device.cuh"
 #include "kernels.h"
 
@@ -138,40 +139,64 @@ void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* 
 // ---------------------------------------------------------------------------------------------------
 // ordered candidate list: one warp per (pair, layer row), hits written at the row's scanned offset in x order
 // ---------------------------------------------------------------------------------------------------
+constexpr int FILL_ROWS = 8;      // consecutive (pair, layer) rows per warp
+
 __global__ void k_fill_candidates(Geom g, const uint8_t* __restrict__ S, CandBuf cb) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int total_rows = g.F * g.rows;
     if (warp == 0 && lane == 0 && cb.row_count[total_rows] > (uint32_t)g.cand_cap) atomicOr(&cb.counters[0], 1u);
-    if (warp >= total_rows) return;
-    const uint32_t begin = cb.row_count[warp], end = cb.row_count[warp + 1];
-    if (begin == end) return;
-    const int f = warp / g.rows, rr = warp - f * g.rows;
-    int l = 0;
+    const int row_begin = warp * FILL_ROWS;
+    if (row_begin >= total_rows) return;
+    const int row_end = min(row_begin + FILL_ROWS, total_rows);
+    // the 9 offsets of this warp's rows, one per lane
+    const uint32_t my_off = cb.row_count[min(row_begin + lane, total_rows)];
+    if (__shfl_sync(0xffffffffu, my_off, 0) == __shfl_sync(0xffffffffu, my_off, row_end - row_begin)) return;   // no hits at all
+    for (int rowi = row_begin; rowi < row_end; rowi++) {
+        const uint32_t begin = __shfl_sync(0xffffffffu, my_off, rowi - row_begin);
+        const uint32_t end = __shfl_sync(0xffffffffu, my_off, rowi - row_begin + 1);
+        if (begin == end) continue;
+        const int f = rowi / g.rows, rr = rowi - f * g.rows;
+        int l = 0;
 #pragma unroll
-    for (int k = 1; k < N_LAYERS; k++) l += (rr >= g.L[k].row0);
-    const LayerGeom& L = g.L[l];
-    const int y = rr - L.row0;
-    const uint8_t* row = S + L.base + (size_t)f * L.px + y * L.w;
-    uint32_t pos = begin;
-    for (int x0 = 0; x0 < L.w; x0 += 32) {
-        const int x = x0 + lane;
-        const bool hit = x < L.w && row[x] >= BRISK_THRESHOLD;
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-            const uint32_t at = pos + __popc(m & ((1u << lane) - 1u));
-            if (at < (uint32_t)g.cand_cap) {
-                cb.xy[at] = (uint32_t)x | ((uint32_t)y << 16);
-                cb.meta[at] = ((uint32_t)f << 3) | (uint32_t)l;
-                cb.flags[at] = 0;
+        for (int k = 1; k < N_LAYERS; k++) l += (rr >= g.L[k].row0);
+        const LayerGeom& L = g.L[l];
+        const int y = rr - L.row0;
+        const uint8_t* row = S + L.base + (size_t)f * L.px + y * L.w;
+        uint32_t pos = begin;
+        // 4 pixels per lane and step (unaligned 32-bit reads built from aligned loads), hits kept in x order
+        for (int x0 = 0; x0 < L.w && pos < end; x0 += 128) {
+            const int x = x0 + 4 * lane;
+            uint32_t v = x < L.w ? load4(row + x) : 0u;
+            unsigned mask = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (((v >> (8 * k)) & 0xffu) >= (unsigned)BRISK_THRESHOLD && x + k < L.w) mask |= 1u << k;
+            const int cnt = __popc(mask);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int nb = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += nb;
             }
+            uint32_t at = pos + (uint32_t)(incl - cnt);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (mask & (1u << k)) {
+                    if (at < (uint32_t)g.cand_cap) {
+                        cb.xy[at] = (uint32_t)(x + k) | ((uint32_t)y << 16);
+                        cb.meta[at] = ((uint32_t)f << 3) | (uint32_t)l;
+                        cb.flags[at] = 0;
+                    }
+                    at++;
+                }
+            pos += (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
         }
-        pos += __popc(m);
     }
 }
 
 void launch_fill_candidates(cudaStream_t st, const Geom& g, const uint8_t* S, CandBuf cb) {
-    const int warps = g.F * g.rows;
+    const int warps = (g.F * g.rows + FILL_ROWS - 1) / FILL_ROWS;
     const int blocks = (warps * 32 + 255) / 256;
     k_fill_candidates<<<blocks, 256, 0, st>>>(g, S, cb);
 }
@@ -258,19 +283,24 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_blocks(uint32_t* data, int n_max, const uint32_t* d_n, uint32_t* partial) {
     const int n = d_n ? min((int)*d_n, n_max) : n_max;
-    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS], sum = 0;
+    const int tiles = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int base = tile * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS], sum = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? data[base + k] : 0; sum += v[k]; }
-    uint32_t total;
-    uint32_t run = block_exclusive_scan(sum, &total);
+        for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? data[base + k] : 0; sum += v[k]; }
+        uint32_t total;
+        uint32_t run = block_exclusive_scan(sum, &total);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) data[base + k] = run; run += v[k]; }
-    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+        for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) data[base + k] = run; run += v[k]; }
+        if (threadIdx.x == 0) partial[tile] = total;
+    }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(uint32_t* partial, int n_blocks) {
-    // single block, serial over chunks of SCAN_BLOCK partials
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(uint32_t* partial, int n_max, const uint32_t* d_n) {
+    // single block, serial over chunks of SCAN_BLOCK partials; partial[tiles] receives the grand total
+    const int n = d_n ? min((int)*d_n, n_max) : n_max;
+    const int n_blocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     __shared__ uint32_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -290,22 +320,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(uint32_t* partia
     if (threadIdx.x == 0) partial[n_blocks] = carry_s;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* data, int n_max, const uint32_t* d_n, const uint32_t* partial,
-                                                           int n_blocks) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* data, int n_max, const uint32_t* d_n, const uint32_t* partial) {
     const int n = d_n ? min((int)*d_n, n_max) : n_max;
-    const uint32_t add = partial[blockIdx.x];
-    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    const int tiles = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t add = partial[tile];
+        const int base = tile * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++)
-        if (base + k < n) data[base + k] += add;
-    if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = partial[n_blocks];
+        for (int k = 0; k < SCAN_ITEMS; k++)
+            if (base + k < n) data[base + k] += add;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = partial[tiles];
 }
 
 void launch_exclusive_scan(cudaStream_t st, uint32_t* data, int n, const uint32_t* d_n, uint32_t* scratch) {
-    const int n_blocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    k_scan_blocks<<<n_blocks, SCAN_THREADS, 0, st>>>(data, n, d_n, scratch);
-    k_scan_partials<<<1, SCAN_THREADS, 0, st>>>(scratch, n_blocks);
-    k_scan_add<<<n_blocks, SCAN_THREADS, 0, st>>>(data, n, d_n, scratch, n_blocks);
+    const int tiles = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    const int grid = tiles < 148 * 8 ? (tiles > 0 ? tiles : 1) : 148 * 8;      // the live length may be far below the bound
+    k_scan_blocks<<<grid, SCAN_THREADS, 0, st>>>(data, n, d_n, scratch);
+    k_scan_partials<<<1, SCAN_THREADS, 0, st>>>(scratch, n, d_n);
+    k_scan_add<<<grid, SCAN_THREADS, 0, st>>>(data, n, d_n, scratch);
 }
 
 }  // namespace mfk

@@ -7,6 +7,7 @@
 // Lanes own receptive fields (43 box means from the integral image), orientation pairs, pair tests and SSD
 // tests; bits are packed with __ballot_sync, whose lane order is laid out so that the ballot words ARE the
 // descriptor bytes.  Compiled with -fmad=false: the orientation angle must round exactly as on the host.
+#include "brisk_device.cuh"
 #include "desc_device.cuh"
 
 namespace mfk {
@@ -18,7 +19,10 @@ struct RowOut { float x, y; int32_t frame; float scale; uint32_t app[2]; uint32_
 constexpr int DW = 8;                 // warps per block
 constexpr int PATCH_PX = PATCH * PATCH, PATCH_PAD = 368;
 
+constexpr int ROI_MAX = 32;           // regions of interest up to this side are staged in shared memory
+
 struct WarpScratch {
+    alignas(4) uint8_t roi[2][ROI_MAX * ROI_MAX];
     uint8_t cur[PATCH_PAD], prev[PATCH_PAD];
     uint8_t field[2][44];             // receptive-field means: unrotated, rotated
     ResizeTap tap[PATCH];             // per destination index; the same table serves rows and columns
@@ -32,10 +36,27 @@ __device__ __forceinline__ void resize_roi_pair(WarpScratch& ws, const uint8_t* 
     __syncwarp();
     const uint8_t* c0 = cur + (size_t)tl_y * W + tl_x;
     const uint8_t* p0 = prev + (size_t)tl_y * W + tl_x;
-    for (int o = lane; o < PATCH_PX; o += 32) {
-        const int dy = o / PATCH, dx = o - dy * PATCH;
-        ws.cur[o] = (uint8_t)resize_px(c0, W, s, ws.tap[dy], ws.tap[dx]);
-        ws.prev[o] = (uint8_t)resize_px(p0, W, s, ws.tap[dy], ws.tap[dx]);
+    if (s <= ROI_MAX) {
+        // stage both regions with 32-bit reads (8 lanes per row, 4 rows per step), then interpolate from shared memory
+        for (int i = lane; i < s * 8; i += 32) {
+            const int r = i >> 3, c4 = (i & 7) * 4;
+            if (c4 < s) {
+                *reinterpret_cast<uint32_t*>(&ws.roi[0][r * ROI_MAX + c4]) = load4(c0 + r * W + c4);
+                *reinterpret_cast<uint32_t*>(&ws.roi[1][r * ROI_MAX + c4]) = load4(p0 + r * W + c4);
+            }
+        }
+        __syncwarp();
+        for (int o = lane; o < PATCH_PX; o += 32) {
+            const int dy = o / PATCH, dx = o - dy * PATCH;
+            ws.cur[o] = (uint8_t)resize_px(ws.roi[0], ROI_MAX, s, ws.tap[dy], ws.tap[dx]);
+            ws.prev[o] = (uint8_t)resize_px(ws.roi[1], ROI_MAX, s, ws.tap[dy], ws.tap[dx]);
+        }
+    } else {
+        for (int o = lane; o < PATCH_PX; o += 32) {
+            const int dy = o / PATCH, dx = o - dy * PATCH;
+            ws.cur[o] = (uint8_t)resize_px(c0, W, s, ws.tap[dy], ws.tap[dx]);
+            ws.prev[o] = (uint8_t)resize_px(p0, W, s, ws.tap[dy], ws.tap[dx]);
+        }
     }
     __syncwarp();
 }

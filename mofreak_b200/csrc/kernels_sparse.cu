@@ -174,13 +174,13 @@ void launch_phase_b(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTa
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_keep_flags(Geom g, CandBuf cb) {
     const uint32_t n = min(cb.row_count[g.F * g.rows], (uint32_t)g.cand_cap);
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) cb.counters[3] = n;                       // live length for the scan
-    if (i < n) cb.keep_scan[i] = (cb.flags[i] & ST_KEEP) ? 1u : 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cb.counters[3] = n;                       // live length for the scan
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        cb.keep_scan[i] = (cb.flags[i] & ST_KEEP) ? 1u : 0u;
 }
 
 void launch_keep_flags(cudaStream_t st, const Geom& g, CandBuf cb) {
-    k_keep_flags<<<(g.cand_cap + 255) / 256, 256, 0, st>>>(g, cb);
+    k_keep_flags<<<148 * 8, 256, 0, st>>>(g, cb);
 }
 
 }  // namespace mfk
@@ -191,17 +191,17 @@ namespace mfk {
 // kept candidates between the pair's first and one-past-last candidate
 __global__ void k_scatter_rows(Geom g, CandBuf cb, uint32_t* __restrict__ pair_rows) {
     const uint32_t n = cb.counters[3];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && (cb.flags[i] & ST_KEEP)) cb.row_src[cb.keep_scan[i]] = i;
-    if (i < (uint32_t)g.F) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < n; i += nthreads)
+        if (cb.flags[i] & ST_KEEP) cb.row_src[cb.keep_scan[i]] = i;
+    for (uint32_t i = tid; i < (uint32_t)g.F; i += nthreads) {
         const uint32_t b = min(cb.row_count[(size_t)i * g.rows], n), e = min(cb.row_count[(size_t)(i + 1) * g.rows], n);
         pair_rows[cb.counters[2] + i] = cb.keep_scan[e] - cb.keep_scan[b];
     }
 }
 
 void launch_scatter_rows(cudaStream_t st, const Geom& g, CandBuf cb, uint32_t* pair_rows) {
-    const int n = g.cand_cap > g.F ? g.cand_cap : g.F;
-    k_scatter_rows<<<(n + 255) / 256, 256, 0, st>>>(g, cb, pair_rows);
+    k_scatter_rows<<<148 * 8, 256, 0, st>>>(g, cb, pair_rows);
 }
 
 __global__ void k_advance(Geom g, CandBuf cb) {
