@@ -195,7 +195,7 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
     CU(c, cudaMemsetAsync(c->cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
     { Span s(c, P_ABSDIFF, 1);   launch_absdiff(st, g, c->store, c->store_frames, pl, c->maps.img); }
     { Span s(c, P_PYRAMID, 5);   launch_pyramid(st, g, c->maps.img); }
-    { Span s(c, P_SCORES, 6);    launch_scores(st, g, c->maps.img, c->maps.S, c->cb.row_count); }
+    { Span s(c, P_SCORES, 1);    launch_scores(st, g, c->maps.img, c->maps.S, c->cb.row_count); }
     { Span s(c, P_SCAN, 3);      launch_exclusive_scan(st, c->cb.row_count, F * g.rows, nullptr, c->scan_scratch); }
     { Span s(c, P_FILL, 1);      launch_fill_candidates(st, g, c->maps.S, c->cb); }
     { Span s(c, P_INTEGRAL, 2);  launch_integral(st, g, c->maps.img, c->integral); }

@@ -91,49 +91,82 @@ void launch_pyramid(cudaStream_t st, const Geom& g, uint8_t* img) {
 //     min_k v_k - p            = low  half of min_k X_k, minus p
 //     p - max_k v_k            = high half of min_k X_k, minus (255 - p)
 // 16 + 16 packed min3 build all 16 arc minima (windows of 3, then 3 of those), 8 packed max3 reduce them.
-constexpr int SC_TX = 32, SC_TY = 8, SC_HALO = 3;
-constexpr int SC_SW = SC_TX + 2 * SC_HALO, SC_SH = SC_TY + 2 * SC_HALO;
+// One launch covers all six layers of all pairs: blockIdx.x enumerates 64x32 tiles over the pair's pyramid,
+// blockIdx.y is the pair.  A block of 256 threads (32 x 8) stages the tile plus its 3-px halo (aligned 32-bit global
+// reads, 128-bit shared stores, 4 packed pixels each) and every thread scores 2 x 4 pixels.
+constexpr int SC_TW = 64, SC_TH = 32;                 // output tile
+constexpr int SC_SW = SC_TW + 8, SC_SH = SC_TH + 6;   // staged: columns x0-4 .. x0+67, rows y0-3 .. y0+34
+constexpr int SC_WORDS = SC_SW / 4;                   // aligned words per staged row
 
-__global__ void __launch_bounds__(SC_TX* SC_TY)
-k_scores(const uint8_t* __restrict__ img_base, uint8_t* __restrict__ S_base, uint32_t* __restrict__ row_count, int w, int h,
-         int px, int row0, int rows_per_pair) {
-    __shared__ uint32_t tile[SC_SH][SC_SW];
-    const int f = blockIdx.z;
-    const uint8_t* img = img_base + (size_t)f * px;
-    const int x0 = blockIdx.x * SC_TX, y0 = blockIdx.y * SC_TY;
-    const int tid = threadIdx.y * SC_TX + threadIdx.x;
-    for (int i = tid; i < SC_SH * SC_SW; i += SC_TX * SC_TY) {
-        const int sy = i / SC_SW, sx = i - sy * SC_SW;
-        const int gx = min(max(x0 + sx - SC_HALO, 0), w - 1);
-        const int gy = min(max(y0 + sy - SC_HALO, 0), h - 1);
-        const uint32_t v = img[gy * w + gx];
-        tile[sy][sx] = v | ((255u - v) << 16);
+struct ScoreTiles { int first[N_LAYERS + 1]; int across[N_LAYERS]; };   // tile index ranges per layer
+
+__global__ void __launch_bounds__(256)
+k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tiles, const uint8_t* __restrict__ img_all,
+         uint8_t* __restrict__ S_all, uint32_t* __restrict__ row_count) {
+    __shared__ __align__(16) uint32_t tile[SC_SH][SC_SW];
+    const int f = blockIdx.y;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < N_LAYERS; k++) l += ((int)blockIdx.x >= tiles.first[k]);
+    const LayerGeom& L = g.L[l];
+    const int t = blockIdx.x - tiles.first[l];
+    const int x0 = (t % tiles.across[l]) * SC_TW, y0 = (t / tiles.across[l]) * SC_TH;
+    const int w = L.w, h = L.h;
+    const uint8_t* img = img_all + L.base + (size_t)f * L.px;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    // ---- stage: word k of staged row r holds pixels x0-4+4k .. x0-1+4k of image row y0-3+r ----
+    for (int i = tid; i < SC_SH * SC_WORDS; i += 256) {
+        const int r = i / SC_WORDS, k = i - r * SC_WORDS;
+        const int gy = min(max(y0 - 3 + r, 0), h - 1);
+        const int gx = x0 - 4 + 4 * k;
+        // pixels left of the image or right of its last row are never used by a scored (interior) pixel; skip the read
+        uint32_t v = 0;
+        if (gx >= 0 && gx < w) v = load4(img + gy * w + gx);
+        uint4 q;
+        q.x = 0x00ff0000u - (v & 0xffu) * 65535u;                 // b | (255 - b) << 16
+        q.y = 0x00ff0000u - ((v >> 8) & 0xffu) * 65535u;
+        q.z = 0x00ff0000u - ((v >> 16) & 0xffu) * 65535u;
+        q.w = 0x00ff0000u - (v >> 24) * 65535u;
+        *reinterpret_cast<uint4*>(&tile[r][4 * k]) = q;
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    const int cx = threadIdx.x + SC_HALO, cy = threadIdx.y + SC_HALO;
-    // ring in circle order (oast9_16.h:214-232)
-    uint32_t r[16];
-    r[0] = tile[cy][cx - 3];      r[1] = tile[cy - 1][cx - 3];  r[2] = tile[cy - 2][cx - 2];  r[3] = tile[cy - 3][cx - 1];
-    r[4] = tile[cy - 3][cx];      r[5] = tile[cy - 3][cx + 1];  r[6] = tile[cy - 2][cx + 2];  r[7] = tile[cy - 1][cx + 3];
-    r[8] = tile[cy][cx + 3];      r[9] = tile[cy + 1][cx + 3];  r[10] = tile[cy + 2][cx + 2]; r[11] = tile[cy + 3][cx + 1];
-    r[12] = tile[cy + 3][cx];     r[13] = tile[cy + 3][cx - 1]; r[14] = tile[cy + 2][cx - 2]; r[15] = tile[cy + 1][cx - 3];
-    int s = oast_score_packed(r, tile[cy][cx]);
-    const bool inside = (x >= 3 && y >= 3 && x < w - 3 && y < h - 3);
-    if (!inside) s = 0;
-    if (x < w && y < h) S_base[(size_t)f * px + y * w + x] = (uint8_t)s;
-    // one warp = one tile row: count its hits with a ballot
-    const unsigned hits = __ballot_sync(0xffffffffu, inside && s >= BRISK_THRESHOLD);
-    if (threadIdx.x == 0 && hits && y < h) atomicAdd(&row_count[(size_t)f * rows_per_pair + row0 + y], __popc(hits));
+    uint8_t* S = S_all + L.base + (size_t)f * L.px;
+#pragma unroll
+    for (int jy = 0; jy < SC_TH / 8; jy++) {
+        const int ly = threadIdx.y + 8 * jy;
+        const int y = y0 + ly, cy = ly + 3;
+        unsigned row_hits = 0;
+#pragma unroll
+        for (int jx = 0; jx < SC_TW / 32; jx++) {
+            const int lx = threadIdx.x + 32 * jx;
+            const int x = x0 + lx, cx = lx + 4;
+            // ring in circle order (oast9_16.h:214-232)
+            uint32_t r[16];
+            r[0] = tile[cy][cx - 3];      r[1] = tile[cy - 1][cx - 3];  r[2] = tile[cy - 2][cx - 2];  r[3] = tile[cy - 3][cx - 1];
+            r[4] = tile[cy - 3][cx];      r[5] = tile[cy - 3][cx + 1];  r[6] = tile[cy - 2][cx + 2];  r[7] = tile[cy - 1][cx + 3];
+            r[8] = tile[cy][cx + 3];      r[9] = tile[cy + 1][cx + 3];  r[10] = tile[cy + 2][cx + 2]; r[11] = tile[cy + 3][cx + 1];
+            r[12] = tile[cy + 3][cx];     r[13] = tile[cy + 3][cx - 1]; r[14] = tile[cy + 2][cx - 2]; r[15] = tile[cy + 1][cx - 3];
+            int s = oast_score_packed(r, tile[cy][cx]);
+            const bool inside = (x >= 3 && y >= 3 && x < w - 3 && y < h - 3);
+            if (!inside) s = 0;
+            if (x < w && y < h) S[y * w + x] = (uint8_t)s;
+            // one warp = one tile row segment: count its hits with a ballot
+            row_hits += __popc(__ballot_sync(0xffffffffu, inside && s >= BRISK_THRESHOLD));
+        }
+        if (threadIdx.x == 0 && row_hits && y < h) atomicAdd(&row_count[(size_t)f * g.rows + L.row0 + y], row_hits);
+    }
 }
 
 void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* S, uint32_t* row_count) {
+    ScoreTiles tiles;
+    int total = 0;
     for (int l = 0; l < N_LAYERS; l++) {
-        const LayerGeom& L = g.L[l];
-        dim3 block(SC_TX, SC_TY);
-        dim3 grid((L.w + SC_TX - 1) / SC_TX, (L.h + SC_TY - 1) / SC_TY, g.F);
-        k_scores<<<grid, block, 0, st>>>(img + L.base, S + L.base, row_count, L.w, L.h, L.px, L.row0, g.rows);
+        tiles.first[l] = total;
+        tiles.across[l] = (g.L[l].w + SC_TW - 1) / SC_TW;
+        total += tiles.across[l] * ((g.L[l].h + SC_TH - 1) / SC_TH);
     }
+    tiles.first[N_LAYERS] = total;
+    k_scores<<<dim3(total, g.F), dim3(32, 8), 0, st>>>(g, tiles, img, S, row_count);
 }
 
 // ---------------------------------------------------------------------------------------------------
