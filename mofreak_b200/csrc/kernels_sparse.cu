@@ -19,18 +19,24 @@ namespace mfk {
 // ---------------------------------------------------------------------------------------------------
 // phase A
 // ---------------------------------------------------------------------------------------------------
-// Two steps per chunk of PA_CHUNK candidates, so that the expensive part runs on full warps:
+// Four steps per chunk of PA_CHUNK candidates, re-packing the survivors between them so that every expensive step
+// runs on (nearly) full warps:
 //   1. every thread tests PA_ITEMS candidates against their 8 neighbours (3 aligned row loads each); losers are
 //      final, candidates with an equal neighbour go to the pair's tie list, the rest to a shared-memory queue;
-//   2. the block drains the queue, one thread per surviving candidate (scans, refinement, keypoint record).
-constexpr int PA_THREADS = 128, PA_ITEMS = 8, PA_CHUNK = PA_THREADS * PA_ITEMS;
+//   2. scan of the layer above (stage_above) for the queue; 3. scan of the layer below (stage_below) for what is left;
+//   4. refinement and keypoint record (stage_emit) for the survivors.
+constexpr int PA_THREADS = 128, PA_ITEMS = 4, PA_CHUNK = PA_THREADS * PA_ITEMS;
+
+struct PaItem { uint32_t c; Scan up; Scan dn; };
 
 __global__ void __launch_bounds__(PA_THREADS) k_phase_a(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
-    __shared__ uint32_t queue[PA_CHUNK];
-    __shared__ int q_n;
+    __shared__ uint32_t queue0[PA_CHUNK];
+    __shared__ PaItem queue1[PA_CHUNK];
+    __shared__ uint32_t queue2[PA_CHUNK];       // indices into queue1
+    __shared__ int q_n[3];
     const uint32_t n = min(cb.row_count[g.F * g.rows], (uint32_t)g.cand_cap);
     for (uint32_t base = blockIdx.x * PA_CHUNK; base < n; base += gridDim.x * PA_CHUNK) {
-        if (threadIdx.x == 0) q_n = 0;
+        if (threadIdx.x < 3) q_n[threadIdx.x] = 0;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < PA_ITEMS; k++) {
@@ -56,15 +62,36 @@ __global__ void __launch_bounds__(PA_THREADS) k_phase_a(const __grid_constant__ 
                 if (slot < PEND_CAP) cb.pend_list[(size_t)(f * N_LAYERS + li) * PEND_CAP + slot] = c;
                 continue;
             }
-            queue[atomicAdd(&q_n, 1)] = c;
+            queue0[atomicAdd(&q_n[0], 1)] = c;
         }
         __syncthreads();
-        const int qn = q_n;
-        for (int i = threadIdx.x; i < qn; i += PA_THREADS) {
-            const uint32_t c = queue[i];
+        for (int i = threadIdx.x; i < q_n[0]; i += PA_THREADS) {
+            const uint32_t c = queue0[i];
             const uint32_t xy = cb.xy[c], meta = cb.meta[c];
             PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
-            after_max2d(pv, cb, tb, meta & 7, xy & 0xffff, xy >> 16, c);
+            Scan up;
+            if (stage_above(pv, cb, meta & 7, xy & 0xffff, xy >> 16, c, up)) {
+                const int slot = atomicAdd(&q_n[1], 1);
+                queue1[slot].c = c; queue1[slot].up = up;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < q_n[1]; i += PA_THREADS) {
+            const uint32_t c = queue1[i].c;
+            const uint32_t xy = cb.xy[c], meta = cb.meta[c];
+            PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
+            Scan dn;
+            if (stage_below(pv, cb, meta & 7, xy & 0xffff, xy >> 16, c, dn)) {
+                queue1[i].dn = dn;
+                queue2[atomicAdd(&q_n[2], 1)] = (uint32_t)i;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < q_n[2]; i += PA_THREADS) {
+            const PaItem it = queue1[queue2[i]];
+            const uint32_t xy = cb.xy[it.c], meta = cb.meta[it.c];
+            PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
+            stage_emit(pv, cb, tb, meta & 7, xy & 0xffff, xy >> 16, it.c, it.up, it.dn);
         }
         __syncthreads();
     }

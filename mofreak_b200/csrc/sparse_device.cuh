@@ -29,52 +29,67 @@ __device__ __forceinline__ int freak_scale_index(const float* __restrict__ thr, 
     return idx;
 }
 
-// Everything after a successful isMax2D for candidate c = (x, y) on layer li: the scans, and for survivors the
-// refined keypoint.  Writes the candidate's final status byte and, for keypoints, its record.
-// All global reads are issued up front: the 3x3 own-layer patch, a 4x4 window of the layer above and of the layer
-// below (Window4) and, on layer 0, the 5x5 image window of the AGAST-5/8 stand-in scores.
-__device__ inline void after_max2d(const PairView& pv, const CandBuf& cb, const DeviceTables& tb, int li, int x, int y, uint32_t c) {
+// What follows a successful isMax2D for candidate c = (x, y) on layer li, in three stages so that the kernels can
+// re-pack the surviving candidates onto full warps between them (about half drop out at each scan):
+//   stage_above  getScoreMaxAbove incl. its write-back marks       (refine3D, brisk.cpp:945-950)
+//   stage_below  getScoreMaxBelow                                   (:988-991, :1053-1056; top layer :654-658)
+//   stage_emit   own 3x3 patch, layer-0 AGAST stand-in, scale/position refinement, keypoint record, FREAK border test
+// Every stage fetches what it needs up front as register windows (Window4, 3x3 patch rows, 5x5 image window).
+struct ScanPair { Scan up, dn; };
+
+__device__ __forceinline__ Scan neutral_scan() { Scan s; s.ismax = true; s.max = 0.f; s.dx = 0.f; s.dy = 0.f; return s; }
+
+__device__ __forceinline__ void finish_failed(const PairView& pv, const CandBuf& cb, int li, int x, int y, uint32_t c) {
+    pv.m.status[pv.off(li) + y * pv.g->L[li].w + x] = ST_PASS2D;
+    cb.flags[c] = ST_PASS2D;
+}
+
+// returns false when a larger score exists above (the candidate is then final)
+__device__ inline bool stage_above(const PairView& pv, const CandBuf& cb, int li, int x, int y, uint32_t c, Scan& up) {
+    up = neutral_scan();
+    if (li == N_LAYERS - 1) return true;
+    const Geom& g = *pv.g;
+    const int center = pv.m.S[pv.off(li) + y * g.L[li].w + x];
+    const Footprint fa = scan_footprint(false, li, x, y);
+    Window4 wa;
+    wa.load(pv.m.S + pv.off(li + 1), g.L[li + 1].w, g.L[li + 1].h, window_origin(fa.x_1, fa.x1), window_origin(fa.y_1, fa.y1));
+    up = scan_neighbour(wa, fa, false, li, x, y, center);
+    wa.flush_marks(pv.m.seen + pv.off(li + 1));             // getScoreMaxAbove's write-backs, even on early exit
+    if (!up.ismax) { finish_failed(pv, cb, li, x, y, c); return false; }
+    return true;
+}
+
+// returns false when a larger score exists below
+__device__ inline bool stage_below(const PairView& pv, const CandBuf& cb, int li, int x, int y, uint32_t c, Scan& dn) {
+    dn = neutral_scan();
+    if (li == 0) return true;
+    const Geom& g = *pv.g;
+    const int center = pv.m.S[pv.off(li) + y * g.L[li].w + x];
+    const Footprint fb = scan_footprint(true, li, x, y);
+    Window4 wb;
+    wb.load(pv.m.S + pv.off(li - 1), g.L[li - 1].w, g.L[li - 1].h, window_origin(fb.x_1, fb.x1), window_origin(fb.y_1, fb.y1));
+    dn = scan_neighbour(wb, fb, true, li, x, y, center);
+    if (!dn.ismax) { finish_failed(pv, cb, li, x, y, c); return false; }
+    return true;
+}
+
+__device__ inline void stage_emit(const PairView& pv, const CandBuf& cb, const DeviceTables& tb, int li, int x, int y, uint32_t c,
+                                  const Scan up, const Scan dn) {
     const Geom& g = *pv.g;
     const LayerGeom& L = g.L[li];
     const uint8_t* Sown = pv.m.S + pv.off(li);
     uint8_t* status = pv.m.status + pv.off(li) + y * L.w + x;
-    uint8_t st = ST_PASS2D;
-
     // own-layer 3x3 patch (the dense map already holds 0 inside the 3-px border, as getAgastScore returns there)
     const uint32_t p0 = load4(Sown + (y - 1) * L.w + x - 1), p1 = load4(Sown + y * L.w + x - 1), p2 = load4(Sown + (y + 1) * L.w + x - 1);
-    const bool has_above = li < N_LAYERS - 1, has_below = li > 0;
-    Window4 wa, wb;
-    Footprint fa, fb;
-    if (has_above) {
-        fa = scan_footprint(false, li, x, y);
-        wa.load(pv.m.S + pv.off(li + 1), g.L[li + 1].w, g.L[li + 1].h, window_origin(fa.x_1, fa.x1), window_origin(fa.y_1, fa.y1));
-    }
-    if (has_below) {
-        fb = scan_footprint(true, li, x, y);
-        wb.load(pv.m.S + pv.off(li - 1), g.L[li - 1].w, g.L[li - 1].h, window_origin(fb.x_1, fb.x1), window_origin(fb.y_1, fb.y1));
-    }
     int a58[9];
     if (li == 0) agast58_patch9(pv.m.img + pv.off(0), L.w, x, y, a58);
+    uint8_t st = ST_PASS2D | ST_SURVIVE;
+    *status = st;       // from here on the candidate's own 3x3 patch counts as touched
 
     const int s_0_0 = p0 & 0xff, s_1_0 = (p0 >> 8) & 0xff, s_2_0 = (p0 >> 16) & 0xff;
     const int s_0_1 = p1 & 0xff, s_1_1 = (p1 >> 8) & 0xff, s_2_1 = (p1 >> 16) & 0xff;
     const int s_0_2 = p2 & 0xff, s_1_2 = (p2 >> 8) & 0xff, s_2_2 = (p2 >> 16) & 0xff;
     const int center = s_1_1;
-
-    Scan up, dn;
-    up.ismax = true; up.max = 0.f; up.dx = 0.f; up.dy = 0.f;
-    dn = up;
-    if (has_above) {
-        up = scan_neighbour(wa, fa, false, li, x, y, center);
-        wa.flush_marks(pv.m.seen + pv.off(li + 1));             // getScoreMaxAbove's write-backs, even on early exit
-        if (!up.ismax) { *status = st; cb.flags[c] = st; return; }
-    }
-    if (has_below) {
-        dn = scan_neighbour(wb, fb, true, li, x, y, center);
-        if (!dn.ismax) { *status = st; cb.flags[c] = st; return; }
-    }
-    st |= ST_SURVIVE;
-    *status = st;       // from here on the candidate's own 3x3 patch counts as touched
 
     float delta_x_layer, delta_y_layer;
     const float max_layer = subpixel2D(s_0_0, s_0_1, s_0_2, s_1_0, s_1_1, s_1_2, s_2_0, s_2_1, s_2_2, delta_x_layer, delta_y_layer);
@@ -148,6 +163,14 @@ __device__ inline void after_max2d(const PairView& pv, const CandBuf& cb, const 
         if (!drop) st |= ST_KEEP;
     }
     cb.flags[c] = st;
+}
+
+// the three stages back to back (phase B and the CPU harness; phase A re-packs candidates between the stages)
+__device__ inline void after_max2d(const PairView& pv, const CandBuf& cb, const DeviceTables& tb, int li, int x, int y, uint32_t c) {
+    Scan up, dn;
+    if (!stage_above(pv, cb, li, x, y, c, up)) return;
+    if (!stage_below(pv, cb, li, x, y, c, dn)) return;
+    stage_emit(pv, cb, tb, li, x, y, c, up, dn);
 }
 
 // ---- tie candidates (phase B) ----------------------------------------------------------------------------------
