@@ -43,6 +43,8 @@ struct mfk_ctx {
     cudaStream_t stream = nullptr;        // all kernels, row fetches
     cudaStream_t copy_stream = nullptr;   // frame-ring uploads, so that H2D of the next frames overlaps the kernels of these
     cudaEvent_t upload_done = nullptr;
+    cudaStream_t aux_stream = nullptr;    // the integral image runs beside the detector kernels of the same batch
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     bool upload_pending = false;
     struct ReadRec { int lo = 0, hi = -1; cudaEvent_t ev = nullptr; bool valid = false; };
     ReadRec readers[8];                   // which slot ranges recent launch sequences still read
@@ -109,14 +111,14 @@ cudaEvent_t take_event(mfk_ctx* c) {
 }
 
 struct Span {          // brackets one launcher call with events when profiling is on
-    mfk_ctx* c; int id; cudaEvent_t a = nullptr, b = nullptr;
-    Span(mfk_ctx* c_, int id_, int kernels) : c(c_), id(id_) {
+    mfk_ctx* c; int id; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    Span(mfk_ctx* c_, int id_, int kernels, cudaStream_t st_ = nullptr) : c(c_), id(id_), st(st_ ? st_ : c_->stream) {
         c->launches += kernels;
         c->prof_launches[id] += kernels;
-        if (c->prof_on) { a = take_event(c); b = take_event(c); cudaEventRecord(a, c->stream); }
+        if (c->prof_on) { a = take_event(c); b = take_event(c); cudaEventRecord(a, st); }
     }
     ~Span() {
-        if (a) { cudaEventRecord(b, c->stream); c->spans.push_back(ProfSpan{id, a, b}); }
+        if (a) { cudaEventRecord(b, st); c->spans.push_back(ProfSpan{id, a, b}); }
     }
 };
 
@@ -194,11 +196,15 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
     CU(c, cudaMemsetAsync(c->maps.seen, 0, (size_t)F * g.pyr_px, st));
     CU(c, cudaMemsetAsync(c->cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
     { Span s(c, P_ABSDIFF, 1);   launch_absdiff(st, g, c->store, c->store_frames, pl, c->maps.img); }
+    // the integral image only needs layer 0: fork it onto the side stream, join before the descriptor kernel
+    CU(c, cudaEventRecord(c->aux_fork, st));
+    CU(c, cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
+    { Span s(c, P_INTEGRAL, 2, c->aux_stream);  launch_integral(c->aux_stream, g, c->maps.img, c->integral); }
+    CU(c, cudaEventRecord(c->aux_join, c->aux_stream));
     { Span s(c, P_PYRAMID, 5);   launch_pyramid(st, g, c->maps.img); }
     { Span s(c, P_SCORES, 1);    launch_scores(st, g, c->maps.img, c->maps.S, c->cb.row_count); }
     { Span s(c, P_SCAN, 3);      launch_exclusive_scan(st, c->cb.row_count, F * g.rows, nullptr, c->scan_scratch); }
     { Span s(c, P_FILL, 1);      launch_fill_candidates(st, g, c->maps.S, c->cb); }
-    { Span s(c, P_INTEGRAL, 2);  launch_integral(st, g, c->maps.img, c->integral); }
     { Span s(c, P_PHASE_A, 1);   launch_phase_a(st, g, c->maps, c->cb, c->tb); }
     { Span s(c, P_PHASE_B, 1);   launch_phase_b(st, g, c->maps, c->cb, c->tb); }
     { Span s(c, P_COMPACT, 5);
@@ -206,6 +212,7 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
       launch_exclusive_scan(st, c->cb.keep_scan, c->cand_cap, c->cb.counters + 3, c->scan_scratch);
       launch_scatter_rows(st, g, c->cb, c->pair_rows);
     }
+    CU(c, cudaStreamWaitEvent(st, c->aux_join, 0));
     { Span s(c, P_DESCRIBE, 2);
       launch_describe(st, g, c->store, c->store_frames, pl, c->maps.img, c->integral, c->cb, c->tb, c->rows_buf);
       launch_advance(st, g, c->cb);
@@ -220,6 +227,7 @@ void destroy(mfk_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     drain_spans(c);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->store); cudaFree(c->maps.img); cudaFree(c->maps.S); cudaFree(c->maps.seen); cudaFree(c->maps.status);
@@ -232,6 +240,9 @@ void destroy(mfk_ctx* c) {
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->upload_done) cudaEventDestroy(c->upload_done);
+    if (c->aux_fork) cudaEventDestroy(c->aux_fork);
+    if (c->aux_join) cudaEventDestroy(c->aux_join);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     for (auto& r : c->readers) if (r.ev) cudaEventDestroy(r.ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -287,6 +298,9 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUC(cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming));
+    CUC(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming));
     for (auto& r : c->readers) CUC(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
     CUC(cudaEventCreate(&c->t0));
     CUC(cudaEventCreate(&c->t1));

@@ -77,18 +77,35 @@ __device__ __forceinline__ float atan2f_fdlibm(float y, float x) {
     }
 }
 
-// FREAK::meanIntensity: box mean around one receptive field from the (W+1)-wide integral image
+// FREAK::meanIntensity: box mean around one receptive field from the (W+1)-wide integral image.
+// The reference rounds the box edges as int(float + 0.5) / int(float + 1.5) evaluated in double.  For a non-negative
+// float t that equals trunc(t) + (frac(t) >= 0.5) resp. trunc(t) + 1 + (frac(t) >= 0.5), and frac(t) = t - trunc(t) is
+// exact in float (Sterbenz), so no double arithmetic is needed; t >= 1 holds for every kept keypoint because FREAK's
+// border filter keeps the whole pattern inside the image.  The truncating integer division is done with a float
+// reciprocal estimate corrected by one step (sums are < 2^24, so the estimate is within 1).
+__device__ __forceinline__ int round_half_up_nonneg(float t, int bias) {
+    const int i = (int)t;
+    return i + bias + ((t - (float)i) >= 0.5f ? 1 : 0);
+}
+
 __device__ __forceinline__ int mean_intensity(const int32_t* __restrict__ I, int W1, const FreakPoint P, float kx, float ky) {
     const float xf = P.x + kx;
     const float yf = P.y + ky;
     const float radius = P.sigma;
-    const int x_left = int((double)(xf - radius) + 0.5);
-    const int y_top = int((double)(yf - radius) + 0.5);
-    const int x_right = int((double)(xf + radius) + 1.5);
-    const int y_bottom = int((double)(yf + radius) + 1.5);
-    int v = I[y_bottom * W1 + x_right] - I[y_bottom * W1 + x_left] + I[y_top * W1 + x_left] - I[y_top * W1 + x_right];
-    v = v / ((x_right - x_left) * (y_bottom - y_top));
-    return v & 0xff;
+    const int x_left = round_half_up_nonneg(xf - radius, 0);
+    const int y_top = round_half_up_nonneg(yf - radius, 0);
+    const int x_right = round_half_up_nonneg(xf + radius, 1);
+    const int y_bottom = round_half_up_nonneg(yf + radius, 1);
+    const int v = I[y_bottom * W1 + x_right] - I[y_bottom * W1 + x_left] + I[y_top * W1 + x_left] - I[y_top * W1 + x_right];
+    const int area = (x_right - x_left) * (y_bottom - y_top);
+#ifdef __CUDA_ARCH__
+    int q = (int)__fdividef((float)v, (float)area);
+#else
+    int q = (int)((float)v / (float)area);
+#endif
+    const int r = v - q * area;
+    q += (r >= area) - (r < 0);
+    return q & 0xff;
 }
 
 // ---- cv::resize(ROI s x s -> 19 x 19, INTER_LINEAR, 8-bit) as OpenCV's fixed-point bilinear path computes it ----

@@ -143,7 +143,7 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
 
 void launch_describe(cudaStream_t st, const Geom& g, const uint8_t* store, int store_frames, PairList pl, const uint8_t*,
                      const int32_t* integral, CandBuf cb, DeviceTables tb, void* rows) {
-    k_describe<<<148 * 4, DW * 32, 0, st>>>(g, store, store_frames, pl, integral, cb, tb, (RowOut*)rows);
+    k_describe<<<148 * 6, DW * 32, 0, st>>>(g, store, store_frames, pl, integral, cb, tb, (RowOut*)rows);
 }
 
 // MIP bytes for caller-supplied keypoints on one frame pair (the MotionInterchangePatterns facade).

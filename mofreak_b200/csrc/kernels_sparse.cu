@@ -104,7 +104,7 @@ void launch_phase_a(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTa
 // ---------------------------------------------------------------------------------------------------
 // phase B: one block per pair
 // ---------------------------------------------------------------------------------------------------
-constexpr int PB_THREADS = 128;
+constexpr int PB_THREADS = 256;
 constexpr int PB_LIST = PEND_CAP;  // tie candidates of one (pair, layer) staged in shared memory per sweep
 
 __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
@@ -154,34 +154,39 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
                 __syncthreads();
             }
             __syncthreads();
-            const int nl = n_list;
-            // fixed point over this chunk
-            if (threadIdx.x == 0) n_left = nl;
-            __syncthreads();
-            while (n_left > 0) {
+            // fixed point over this chunk; the list is re-packed after every round so that later rounds stay dense
+            int nl = n_list;
+            while (nl > 0) {
                 for (int i = threadIdx.x; i < nl; i += PB_THREADS) {
-                    verdict[i] = 0;
                     const uint32_t c = list[i];
-                    if (c == 0xffffffffu) continue;
                     const uint32_t xy = cb.xy[c];
                     const int x = xy & 0xffff, y = xy >> 16;
                     TieWindow tw;
                     tw.load(pv, li, x, y);
-                    if (earlier_pending_nearby(tw)) continue;
-                    verdict[i] = tie_break(tw) ? 2 : 1;
+                    verdict[i] = earlier_pending_nearby(tw) ? 0 : (tie_break(tw) ? 2 : 1);
                 }
                 __syncthreads();
-                for (int i = threadIdx.x; i < nl; i += PB_THREADS) {
-                    if (!verdict[i]) continue;
-                    const uint32_t c = list[i];
-                    const uint32_t xy = cb.xy[c];
-                    const int x = xy & 0xffff, y = xy >> 16;
-                    if (verdict[i] == 2) after_max2d(pv, cb, tb, li, x, y, c);
-                    else { pv.m.status[pv.off(li) + y * L.w + x] = 0; cb.flags[c] = 0; }
-                    list[i] = 0xffffffffu;
-                    atomicSub(&n_left, 1);
+                if (threadIdx.x == 0) n_left = 0;
+                __syncthreads();
+                // apply this round's verdicts (they were all taken from the previous round's statuses)
+                for (int i0 = 0; i0 < nl; i0 += PB_THREADS) {
+                    const int i = i0 + threadIdx.x;
+                    uint32_t c = 0;
+                    uint8_t v = 3;
+                    if (i < nl) { c = list[i]; v = verdict[i]; }
+                    if (v == 1 || v == 2) {
+                        const uint32_t xy = cb.xy[c];
+                        const int x = xy & 0xffff, y = xy >> 16;
+                        if (v == 2) after_max2d(pv, cb, tb, li, x, y, c);
+                        else { pv.m.status[pv.off(li) + y * L.w + x] = 0; cb.flags[c] = 0; }
+                    }
+                    __syncthreads();        // every thread has read its list entry before slots are reused
+                    if (v == 0) list[atomicAdd(&n_left, 1)] = c;        // still waiting: keep (order is irrelevant)
+                    __syncthreads();
                 }
                 __threadfence_block();
+                __syncthreads();
+                nl = n_left;
                 __syncthreads();
             }
             cursor = next_cursor;
