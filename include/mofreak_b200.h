@@ -151,6 +151,10 @@ int  mfk_debug_layer(mfk_ctx* ctx, int what, int layer, int pair, uint8_t* out, 
  * layer} floats in reference order; writes at most cap, *n gets the full count. */
 int  mfk_debug_keypoints(mfk_ctx* ctx, int pair, float* out, int cap, int* n);
 
+/* Raw device counters of the context: [0] overflow flags, [1] rows accumulated, [2] pairs accumulated, [3] live candidates of
+ * the last batch, [4..7] optional statistics (builds with -DMFK_PB_STATS: tie-resolution rounds, ties, max rounds, tie visits). */
+int  mfk_debug_counters(mfk_ctx* ctx, uint32_t out[8]);
+
 /* ---- utilities that are not device work ------------------------------------------------------------- */
 
 /* Deterministic synthetic "moving squares" clip (tests, smoke, bench): n_frames of w x h starting at

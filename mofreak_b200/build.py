@@ -48,6 +48,7 @@ def build(force=False, verbose=False, extra=()):
     if not force and not needs_build():
         return LIB
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    extra = list(extra) + os.environ.get("MFK_NVCC_EXTRA", "").split()
     cmd = [nvcc_path(), "-ccbin", host_cxx] + NVCC_FLAGS + list(extra) + ["-shared", "-o", LIB] + sources() + ["-ldl"]
     if verbose:
         print(" ".join(cmd))

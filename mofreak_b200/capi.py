@@ -25,7 +25,7 @@ SYMBOLS = [
     "mfk_extract_pairs", "mfk_fetch_rows", "mfk_rows_device", "mfk_reset_rows", "mfk_extract_clip", "mfk_mip_describe",
     "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram",
     "mfk_allreduce_counts", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read",
-    "mfk_launch_count", "mfk_debug_layer", "mfk_debug_keypoints", "mfk_synth_clip", "mfk_freak_scale_index", "mfk_version",
+    "mfk_launch_count", "mfk_debug_layer", "mfk_debug_keypoints", "mfk_debug_counters", "mfk_synth_clip", "mfk_freak_scale_index", "mfk_version",
 ]
 
 
@@ -78,6 +78,7 @@ def lib():
     L.mfk_launch_count.argtypes = [p]; L.mfk_launch_count.restype = C.c_uint64
     L.mfk_debug_layer.argtypes = [p, C.c_int, C.c_int, C.c_int, u8p, C.POINTER(C.c_int)]
     L.mfk_debug_keypoints.argtypes = [p, C.c_int, f32p, C.c_int, C.POINTER(C.c_int)]
+    L.mfk_debug_counters.argtypes = [p, C.c_void_p]
     L.mfk_synth_clip.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int]; L.mfk_synth_clip.restype = None
     L.mfk_freak_scale_index.argtypes = [C.c_float]
     L.mfk_version.restype = C.c_char_p
@@ -247,6 +248,11 @@ class Context:
         buf = np.zeros(self.width * self.height, np.uint8)
         self._check(self._L.mfk_debug_layer(self._h, what, layer, pair, _ptr(buf), dims))
         return buf[:dims[0] * dims[1]].reshape(dims[1], dims[0]).copy()
+
+    def debug_counters(self):
+        out = np.zeros(8, np.uint32)
+        self._check(self._L.mfk_debug_counters(self._h, _ptr(out)))
+        return out
 
     def debug_keypoints(self, pair, cap=65536):
         out = np.zeros((cap, 5), np.float32)

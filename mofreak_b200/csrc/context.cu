@@ -676,6 +676,14 @@ int mfk_debug_layer(mfk_ctx* c, int what, int layer, int pair, uint8_t* out, int
     return MFK_OK;
 }
 
+int mfk_debug_counters(mfk_ctx* c, uint32_t out[8]) {
+    if (!c || !out) return MFK_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(out, c->cb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return MFK_OK;
+}
+
 int mfk_debug_keypoints(mfk_ctx* c, int pair, float* out, int cap, int* n) {
     if (!c || !n) return fail(c, MFK_ERR_ARG, "bad argument to mfk_debug_keypoints");
     if (!c->have_last || pair < 0 || pair >= c->last.F) return fail(c, MFK_ERR_STATE, "no such pair in the last batch");

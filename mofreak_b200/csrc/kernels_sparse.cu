@@ -156,7 +156,15 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
             __syncthreads();
             // fixed point over this chunk; the list is re-packed after every round so that later rounds stay dense
             int nl = n_list;
+#ifdef MFK_PB_STATS
+            int rounds = 0;
+            if (threadIdx.x == 0) atomicAdd(&cb.counters[5], (uint32_t)nl);
+#endif
             while (nl > 0) {
+#ifdef MFK_PB_STATS
+                rounds++;
+                if (threadIdx.x == 0) { atomicAdd(&cb.counters[4], 1u); atomicAdd(&cb.counters[7], (uint32_t)nl); }
+#endif
                 for (int i = threadIdx.x; i < nl; i += PB_THREADS) {
                     const uint32_t c = list[i];
                     const uint32_t xy = cb.xy[c];
@@ -189,6 +197,9 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
                 nl = n_left;
                 __syncthreads();
             }
+#ifdef MFK_PB_STATS
+            if (threadIdx.x == 0) atomicMax(&cb.counters[6], (uint32_t)rounds);
+#endif
             cursor = next_cursor;
             __syncthreads();
         } while (more);
