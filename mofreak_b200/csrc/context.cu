@@ -43,10 +43,8 @@ struct mfk_ctx {
     cudaStream_t stream = nullptr;        // all kernels, row fetches
     cudaStream_t copy_stream = nullptr;   // frame-ring uploads, so that H2D of the next frames overlaps the kernels of these
     cudaEvent_t upload_done = nullptr;
-    cudaStream_t aux_stream = nullptr;    // the integral image runs beside the detector kernels of the same batch
-    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     bool upload_pending = false;
-    struct ReadRec { int lo = 0, hi = -1; cudaEvent_t ev = nullptr; bool valid = false; };
+    struct ReadRec { int lo = 0, hi = -1; cudaEvent_t ev[2] = {nullptr, nullptr}; bool on[2] = {false, false}; bool valid = false; };
     ReadRec readers[8];                   // which slot ranges recent launch sequences still read
     int reader_next = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -54,10 +52,25 @@ struct mfk_ctx {
     int lw[N_LAYERS], lh[N_LAYERS], rows = 0, pyr_px = 0;
     // device buffers
     uint8_t* store = nullptr;
-    Maps maps{};
-    int32_t* integral = nullptr;
-    CandBuf cb{};
-    uint32_t* scan_scratch = nullptr;
+    // Two complete sets of per-batch buffers ("lanes"), each with its own streams: consecutive launch sequences
+    // alternate between them, so the latency-bound sparse kernels of one batch run beside the issue-bound dense
+    // kernels of the next.  Only the row accumulation (counters, rows_buf, pair_rows) is shared; it is handed from
+    // batch to batch through `advanced` events.
+    struct Lane {
+        Maps maps{};
+        int32_t* integral = nullptr;
+        CandBuf cb{};
+        uint32_t* scan_scratch = nullptr;
+        cudaStream_t stream = nullptr, aux_stream = nullptr;
+        cudaEvent_t aux_fork = nullptr, aux_join = nullptr, advanced = nullptr, done = nullptr;
+        bool used = false;
+    };
+    Lane lane[2];
+    int n_lanes = 2;
+    uint64_t batches = 0;
+    int last_lane = 0;
+    uint32_t* counters = nullptr;
+    cudaEvent_t main_mark = nullptr;
     int cand_cap = 0;
     mfk_row* rows_buf = nullptr;
     size_t row_cap = 0;
@@ -169,11 +182,32 @@ int upload_tables(mfk_ctx* c) {
     return MFK_OK;
 }
 
+// orders everything queued on the lanes before whatever is queued on the main stream next
+int join_lanes(mfk_ctx* c) {
+    for (int i = 0; i < c->n_lanes; i++) {
+        mfk_ctx::Lane& L = c->lane[i];
+        if (!L.used) continue;
+        CU(c, cudaEventRecord(L.done, L.stream));
+        CU(c, cudaStreamWaitEvent(c->stream, L.done, 0));
+    }
+    return MFK_OK;
+}
+
+int sync_all(mfk_ctx* c) {
+    CU(c, cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < c->n_lanes; i++) {
+        if (c->lane[i].aux_stream) CU(c, cudaStreamSynchronize(c->lane[i].aux_stream));
+        if (c->lane[i].stream) CU(c, cudaStreamSynchronize(c->lane[i].stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    return MFK_OK;
+}
+
 int grow_pair_arrays(mfk_ctx* c, size_t need) {
     if (need <= c->pair_cap) return MFK_OK;
     size_t cap = std::max(need, c->pair_cap * 2);
     cap = std::max<size_t>(cap, 1024);
-    CU(c, cudaStreamSynchronize(c->stream));
+    { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
     int32_t *a, *b, *l; uint32_t* pr;
     CU(c, dalloc(&a, cap)); CU(c, dalloc(&b, cap)); CU(c, dalloc(&l, cap)); CU(c, dalloc(&pr, cap));
     if (c->pairs_queued) {
@@ -187,63 +221,74 @@ int grow_pair_arrays(mfk_ctx* c, size_t need) {
     return MFK_OK;
 }
 
-// one launch sequence over `F` pairs whose descriptions start at pair index `first`
+// one launch sequence over `F` pairs whose descriptions start at pair index `first`, on the next lane
 int run_batch(mfk_ctx* c, size_t first, int F) {
     const Geom g = make_geom(c, F);
     PairList pl{c->d_cur + first, c->d_prev + first, c->d_label + first};
-    cudaStream_t st = c->stream;
-    CU(c, cudaMemsetAsync(c->cb.row_count, 0, ((size_t)F * g.rows + 1) * sizeof(uint32_t), st));
-    CU(c, cudaMemsetAsync(c->maps.seen, 0, (size_t)F * g.pyr_px, st));
-    CU(c, cudaMemsetAsync(c->cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
-    { Span s(c, P_ABSDIFF, 1);   launch_absdiff(st, g, c->store, c->store_frames, pl, c->maps.img); }
+    const int li = (int)(c->batches % (uint64_t)c->n_lanes);
+    mfk_ctx::Lane& L = c->lane[li];
+    mfk_ctx::Lane& P = c->lane[c->last_lane];            // lane of the previous batch
+    cudaStream_t st = L.stream;
+    CU(c, cudaMemsetAsync(L.cb.row_count, 0, ((size_t)F * g.rows + 1) * sizeof(uint32_t), st));
+    CU(c, cudaMemsetAsync(L.maps.seen, 0, (size_t)F * g.pyr_px, st));
+    CU(c, cudaMemsetAsync(L.cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
+    { Span s(c, P_ABSDIFF, 1, st);   launch_absdiff(st, g, c->store, c->store_frames, pl, L.maps.img); }
     // the integral image only needs layer 0: fork it onto the side stream, join before the descriptor kernel
-    CU(c, cudaEventRecord(c->aux_fork, st));
-    CU(c, cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
-    { Span s(c, P_INTEGRAL, 2, c->aux_stream);  launch_integral(c->aux_stream, g, c->maps.img, c->integral); }
-    CU(c, cudaEventRecord(c->aux_join, c->aux_stream));
-    { Span s(c, P_PYRAMID, 5);   launch_pyramid(st, g, c->maps.img); }
-    { Span s(c, P_SCORES, 1);    launch_scores(st, g, c->maps.img, c->maps.S, c->cb.row_count); }
-    { Span s(c, P_SCAN, 3);      launch_exclusive_scan(st, c->cb.row_count, F * g.rows, nullptr, c->scan_scratch); }
-    { Span s(c, P_FILL, 1);      launch_fill_candidates(st, g, c->maps.S, c->cb); }
-    { Span s(c, P_PHASE_A, 1);   launch_phase_a(st, g, c->maps, c->cb, c->tb); }
-    { Span s(c, P_PHASE_B, 1);   launch_phase_b(st, g, c->maps, c->cb, c->tb); }
-    { Span s(c, P_COMPACT, 5);
-      launch_keep_flags(st, g, c->cb);
-      launch_exclusive_scan(st, c->cb.keep_scan, c->cand_cap, c->cb.counters + 3, c->scan_scratch);
-      launch_scatter_rows(st, g, c->cb, c->pair_rows);
+    CU(c, cudaEventRecord(L.aux_fork, st));
+    CU(c, cudaStreamWaitEvent(L.aux_stream, L.aux_fork, 0));
+    { Span s(c, P_INTEGRAL, 2, L.aux_stream);  launch_integral(L.aux_stream, g, L.maps.img, L.integral); }
+    CU(c, cudaEventRecord(L.aux_join, L.aux_stream));
+    { Span s(c, P_PYRAMID, 5, st);   launch_pyramid(st, g, L.maps.img); }
+    { Span s(c, P_SCORES, 1, st);    launch_scores(st, g, L.maps.img, L.maps.S, L.cb.row_count); }
+    { Span s(c, P_SCAN, 3, st);      launch_exclusive_scan(st, L.cb.row_count, F * g.rows, nullptr, L.scan_scratch); }
+    { Span s(c, P_FILL, 1, st);      launch_fill_candidates(st, g, L.maps.S, L.cb); }
+    { Span s(c, P_PHASE_A, 1, st);   launch_phase_a(st, g, L.maps, L.cb, c->tb); }
+    { Span s(c, P_PHASE_B, 1, st);   launch_phase_b(st, g, L.maps, L.cb, c->tb); }
+    // from here on the shared row accumulation is touched: wait until the previous batch has advanced it
+    if (c->batches > 0 && c->last_lane != li) CU(c, cudaStreamWaitEvent(st, P.advanced, 0));
+    { Span s(c, P_COMPACT, 5, st);
+      launch_keep_flags(st, g, L.cb);
+      launch_exclusive_scan(st, L.cb.keep_scan, c->cand_cap, L.cb.live, L.scan_scratch);
+      launch_scatter_rows(st, g, L.cb, c->pair_rows);
     }
-    CU(c, cudaStreamWaitEvent(st, c->aux_join, 0));
-    { Span s(c, P_DESCRIBE, 2);
-      launch_describe(st, g, c->store, c->store_frames, pl, c->maps.img, c->integral, c->cb, c->tb, c->rows_buf);
-      launch_advance(st, g, c->cb);
+    CU(c, cudaStreamWaitEvent(st, L.aux_join, 0));
+    { Span s(c, P_DESCRIBE, 2, st);
+      launch_describe(st, g, c->store, c->store_frames, pl, L.maps.img, L.integral, L.cb, c->tb, c->rows_buf);
+      launch_advance(st, g, L.cb);
     }
+    CU(c, cudaEventRecord(L.advanced, st));
     CU(c, cudaGetLastError());
-    c->last = g; c->have_last = true;
+    L.used = true;
+    c->last = g; c->have_last = true; c->last_lane = li;
+    c->batches++;
     return MFK_OK;
 }
 
 void destroy(mfk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+    if (c->stream) sync_all(c);
     drain_spans(c);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
-    cudaFree(c->store); cudaFree(c->maps.img); cudaFree(c->maps.S); cudaFree(c->maps.seen); cudaFree(c->maps.status);
-    cudaFree(c->integral); cudaFree(c->cb.row_count); cudaFree(c->cb.xy); cudaFree(c->cb.meta); cudaFree(c->cb.kx);
-    cudaFree(c->cb.ky); cudaFree(c->cb.ksize); cudaFree(c->cb.kresp); cudaFree(c->cb.flags); cudaFree(c->cb.scale_idx);
-    cudaFree(c->cb.keep_scan); cudaFree(c->cb.row_src); cudaFree(c->cb.pend_count); cudaFree(c->cb.pend_list); cudaFree(c->cb.counters); cudaFree(c->scan_scratch);
+    cudaFree(c->store);
+    for (auto& L : c->lane) {
+        cudaFree(L.maps.img); cudaFree(L.maps.S); cudaFree(L.maps.seen); cudaFree(L.maps.status); cudaFree(L.integral);
+        cudaFree(L.cb.row_count); cudaFree(L.cb.xy); cudaFree(L.cb.meta); cudaFree(L.cb.kx); cudaFree(L.cb.ky); cudaFree(L.cb.ksize);
+        cudaFree(L.cb.kresp); cudaFree(L.cb.flags); cudaFree(L.cb.scale_idx); cudaFree(L.cb.keep_scan); cudaFree(L.cb.row_src);
+        cudaFree(L.cb.pend_count); cudaFree(L.cb.pend_list); cudaFree(L.cb.live); cudaFree(L.scan_scratch);
+        for (cudaEvent_t e : {L.aux_fork, L.aux_join, L.advanced, L.done}) if (e) cudaEventDestroy(e);
+        if (L.aux_stream) cudaStreamDestroy(L.aux_stream);
+        if (L.stream) cudaStreamDestroy(L.stream);
+    }
+    cudaFree(c->counters);
     cudaFree(c->rows_buf); cudaFree(c->pair_rows); cudaFree(c->d_cur); cudaFree(c->d_prev); cudaFree(c->d_label);
     for (void* p : c->tb_alloc) cudaFree(p);
     cudaFree(c->codebook); cudaFree(c->bow_counts); cudaFree(c->bow_tmp);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->upload_done) cudaEventDestroy(c->upload_done);
-    if (c->aux_fork) cudaEventDestroy(c->aux_fork);
-    if (c->aux_join) cudaEventDestroy(c->aux_join);
-    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-    for (auto& r : c->readers) if (r.ev) cudaEventDestroy(r.ev);
+    if (c->main_mark) cudaEventDestroy(c->main_mark);
+    for (auto& r : c->readers) for (cudaEvent_t e : r.ev) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -298,10 +343,16 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUC(cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming));
-    CUC(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-    CUC(cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
-    CUC(cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming));
-    for (auto& r : c->readers) CUC(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&c->main_mark, cudaEventDisableTiming));
+    for (auto& L : c->lane) {
+        CUC(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CUC(cudaStreamCreateWithFlags(&L.aux_stream, cudaStreamNonBlocking));
+        CUC(cudaEventCreateWithFlags(&L.aux_fork, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&L.aux_join, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&L.advanced, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    }
+    for (auto& r : c->readers) for (auto& e : r.ev) CUC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUC(cudaEventCreate(&c->t0));
     CUC(cudaEventCreate(&c->t1));
     // pyramid geometry, brisk.cpp:1660, 1666
@@ -319,23 +370,30 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     CUC(dalloc(&c->store, (size_t)store_frames * px + 64));
     // slack: register windows (brisk_device.cuh Window4 / load5) read up to 4 rows + 8 bytes past a layer's end
     const size_t slack = (size_t)4 * width + 64;
-    CUC(dalloc(&c->maps.img, F * c->pyr_px + slack));
-    CUC(dalloc(&c->maps.S, F * c->pyr_px + slack));
-    CUC(dalloc(&c->maps.seen, F * c->pyr_px + slack));
-    CUC(dalloc(&c->maps.status, F * c->pyr_px + slack));
-    CUC(dalloc(&c->integral, F * (size_t)(width + 1) * (height + 1)));
-    CUC(dalloc(&c->cb.row_count, F * c->rows + 2));
-    CUC(dalloc(&c->cb.xy, cand_cap)); CUC(dalloc(&c->cb.meta, cand_cap));
-    CUC(dalloc(&c->cb.kx, cand_cap)); CUC(dalloc(&c->cb.ky, cand_cap));
-    CUC(dalloc(&c->cb.ksize, cand_cap)); CUC(dalloc(&c->cb.kresp, cand_cap));
-    CUC(dalloc(&c->cb.flags, cand_cap)); CUC(dalloc(&c->cb.scale_idx, cand_cap));
-    CUC(dalloc(&c->cb.keep_scan, cand_cap + 2)); CUC(dalloc(&c->cb.row_src, cand_cap));
-    CUC(dalloc(&c->cb.pend_count, F * N_LAYERS));
-    CUC(dalloc(&c->cb.pend_list, F * N_LAYERS * PEND_CAP));
-    CUC(dalloc(&c->cb.counters, 8));
-    CUC(cudaMemset(c->cb.counters, 0, 8 * sizeof(uint32_t)));
     const size_t scan_n = std::max<size_t>(cand_cap, F * c->rows);
-    CUC(dalloc(&c->scan_scratch, scan_n / 2048 + 8));
+    CUC(dalloc(&c->counters, 8));
+    CUC(cudaMemset(c->counters, 0, 8 * sizeof(uint32_t)));
+    // a context that only ever sees one launch sequence per call (max_pairs >= the caller's batches) still gets both
+    // lanes: consecutive calls alternate as well
+    for (auto& L : c->lane) {
+        CUC(dalloc(&L.maps.img, F * c->pyr_px + slack));
+        CUC(dalloc(&L.maps.S, F * c->pyr_px + slack));
+        CUC(dalloc(&L.maps.seen, F * c->pyr_px + slack));
+        CUC(dalloc(&L.maps.status, F * c->pyr_px + slack));
+        CUC(dalloc(&L.integral, F * (size_t)(width + 1) * (height + 1)));
+        CUC(dalloc(&L.cb.row_count, F * c->rows + 2));
+        CUC(dalloc(&L.cb.xy, cand_cap)); CUC(dalloc(&L.cb.meta, cand_cap));
+        CUC(dalloc(&L.cb.kx, cand_cap)); CUC(dalloc(&L.cb.ky, cand_cap));
+        CUC(dalloc(&L.cb.ksize, cand_cap)); CUC(dalloc(&L.cb.kresp, cand_cap));
+        CUC(dalloc(&L.cb.flags, cand_cap)); CUC(dalloc(&L.cb.scale_idx, cand_cap));
+        CUC(dalloc(&L.cb.keep_scan, cand_cap + 2)); CUC(dalloc(&L.cb.row_src, cand_cap));
+        CUC(dalloc(&L.cb.pend_count, F * N_LAYERS));
+        CUC(dalloc(&L.cb.pend_list, F * N_LAYERS * PEND_CAP));
+        CUC(dalloc(&L.cb.live, 2));
+        CUC(cudaMemset(L.cb.live, 0, 2 * sizeof(uint32_t)));
+        L.cb.counters = c->counters;
+        CUC(dalloc(&L.scan_scratch, scan_n / 2048 + 8));
+    }
     CUC(dalloc(&c->rows_buf, c->row_cap));
     if (upload_tables(c) != MFK_OK) { g_create_error = c->err; destroy(c); return MFK_ERR_CUDA; }
     if (grow_pair_arrays(c, (size_t)max_pairs) != MFK_OK) { g_create_error = c->err; destroy(c); return MFK_ERR_CUDA; }
@@ -350,9 +408,7 @@ const char* mfk_last_error(const mfk_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int mfk_sync(mfk_ctx* c) {
     if (!c) return MFK_ERR_ARG;
-    CU(c, cudaStreamSynchronize(c->copy_stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    return MFK_OK;
+    return sync_all(c);
 }
 
 int mfk_upload_frames(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_frames, int slot0) {
@@ -367,7 +423,8 @@ int mfk_upload_frames(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_fram
         const int run = std::min(n_frames - done, c->store_frames - slot);     // contiguous slots before the wrap
         // slots still being read by queued launch sequences must not be overwritten under them
         for (auto& r : c->readers)
-            if (r.valid && r.lo <= slot + run - 1 && r.hi >= slot) CU(c, cudaStreamWaitEvent(c->copy_stream, r.ev, 0));
+            if (r.valid && r.lo <= slot + run - 1 && r.hi >= slot)
+                for (int k = 0; k < 2; k++) if (r.on[k]) CU(c, cudaStreamWaitEvent(c->copy_stream, r.ev[k], 0));
         const uint8_t* src = gray + (size_t)done * stride * c->H;
         if (stride == (size_t)c->W)
             CU(c, cudaMemcpyAsync(c->store + (size_t)slot * px, src, (size_t)run * px, cudaMemcpyHostToDevice, c->copy_stream));
@@ -395,12 +452,23 @@ int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_s
     int rc = grow_pair_arrays(c, c->pairs_queued + (size_t)n_pairs);
     if (rc != MFK_OK) return rc;
     const size_t first = c->pairs_queued;
-    if (c->upload_pending) { CU(c, cudaStreamWaitEvent(c->stream, c->upload_done, 0)); c->upload_pending = false; }
-    CU(c, cudaMemcpyAsync(c->d_cur + first, cur_slot, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->d_prev + first, prev_slot, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->d_label + first, label, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    // pair descriptions travel on the copy stream, behind any frame uploads; the lanes wait for both through upload_done
+    CU(c, cudaMemcpyAsync(c->d_cur + first, cur_slot, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaMemcpyAsync(c->d_prev + first, prev_slot, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaMemcpyAsync(c->d_label + first, label, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaEventRecord(c->upload_done, c->copy_stream));
+    c->upload_pending = false;
+    // ... and for whatever the caller queued on the main stream before this call (row resets, timers)
+    CU(c, cudaEventRecord(c->main_mark, c->stream));
+    bool touched[2] = {false, false};
     for (int done = 0; done < n_pairs; done += c->max_pairs) {
         const int F = std::min(c->max_pairs, n_pairs - done);
+        const int li = (int)(c->batches % (uint64_t)c->n_lanes);
+        if (!touched[li]) {
+            CU(c, cudaStreamWaitEvent(c->lane[li].stream, c->upload_done, 0));
+            CU(c, cudaStreamWaitEvent(c->lane[li].stream, c->main_mark, 0));
+            touched[li] = true;
+        }
         rc = run_batch(c, first + done, F);
         if (rc != MFK_OK) return rc;
     }
@@ -413,22 +481,28 @@ int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_s
     }
     mfk_ctx::ReadRec& rec = c->readers[c->reader_next];
     c->reader_next = (c->reader_next + 1) % 8;
-    if (rec.valid) CU(c, cudaStreamWaitEvent(c->copy_stream, rec.ev, 0));       // recycled record: keep its ordering
+    if (rec.valid)          // recycled record: keep its ordering
+        for (int k = 0; k < 2; k++) if (rec.on[k]) CU(c, cudaStreamWaitEvent(c->copy_stream, rec.ev[k], 0));
     rec.lo = lo; rec.hi = hi; rec.valid = true;
-    CU(c, cudaEventRecord(rec.ev, c->stream));
+    for (int k = 0; k < 2; k++) {
+        rec.on[k] = touched[k];
+        if (touched[k]) CU(c, cudaEventRecord(rec.ev[k], c->lane[k].stream));
+    }
     return MFK_OK;
 }
 
 static int read_counters(mfk_ctx* c, uint32_t h[4]) {
+    { const int rc = join_lanes(c); if (rc != MFK_OK) return rc; }
     CU(c, cudaStreamSynchronize(c->stream));
-    CU(c, cudaMemcpy(h, c->cb.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(h, c->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return MFK_OK;
 }
 
 int mfk_reset_rows(mfk_ctx* c) {
     if (!c) return MFK_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaMemsetAsync(c->cb.counters, 0, 4 * sizeof(uint32_t), c->stream));
+    { const int rc = join_lanes(c); if (rc != MFK_OK) return rc; }
+    CU(c, cudaMemsetAsync(c->counters, 0, 4 * sizeof(uint32_t), c->stream));
     c->pairs_queued = 0;
     return MFK_OK;
 }
@@ -507,7 +581,7 @@ int mfk_mip_describe(mfk_ctx* c, int cur_slot, int prev_slot, const float* kp_xy
     float* d_kp = (float*)c->bow_tmp;
     uint8_t* d_mot = (uint8_t*)c->bow_tmp + (size_t)n * 12;
     uint32_t* d_err = (uint32_t*)((uint8_t*)c->bow_tmp + err_off);
-    if (c->upload_pending) { CU(c, cudaStreamWaitEvent(c->stream, c->upload_done, 0)); c->upload_pending = false; }
+    CU(c, cudaStreamWaitEvent(c->stream, c->upload_done, 0));
     CU(c, cudaMemcpyAsync(d_kp, kp_xys, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemsetAsync(d_err, 0, 4, c->stream));
     const size_t px = (size_t)c->W * c->H;
@@ -627,6 +701,7 @@ int mfk_timer_start(mfk_ctx* c) {
 int mfk_timer_stop(mfk_ctx* c, float* elapsed_ms) {
     if (!c || !elapsed_ms) return MFK_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
+    { const int rc = join_lanes(c); if (rc != MFK_OK) return rc; }
     CU(c, cudaEventRecord(c->t1, c->stream));
     CU(c, cudaEventSynchronize(c->t1));
     CU(c, cudaEventElapsedTime(elapsed_ms, c->t0, c->t1));
@@ -636,7 +711,7 @@ int mfk_timer_stop(mfk_ctx* c, float* elapsed_ms) {
 int mfk_profile_enable(mfk_ctx* c, int enable) {
     if (!c) return MFK_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->stream));
+    { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
     drain_spans(c);
     c->prof_on = enable != 0;
     memset(c->prof_launches, 0, sizeof c->prof_launches);
@@ -647,7 +722,7 @@ int mfk_profile_enable(mfk_ctx* c, int enable) {
 int mfk_profile_read(mfk_ctx* c, mfk_prof_entry* entries, int cap, int* n_entries) {
     if (!c || !entries || !n_entries) return MFK_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->stream));
+    { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
     drain_spans(c);
     int n = 0;
     for (int i = 0; i < P_COUNT && n < cap; i++) {
@@ -668,9 +743,10 @@ int mfk_debug_layer(mfk_ctx* c, int what, int layer, int pair, uint8_t* out, int
     if (!c || !out || layer < 0 || layer >= N_LAYERS || what < 0 || what > 1) return fail(c, MFK_ERR_ARG, "bad argument to mfk_debug_layer");
     if (!c->have_last || pair < 0 || pair >= c->last.F) return fail(c, MFK_ERR_STATE, "no such pair in the last batch");
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->stream));
+    { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
     const LayerGeom& L = c->last.L[layer];
-    const uint8_t* base = (what == 0 ? c->maps.img : c->maps.S) + L.base + (size_t)pair * L.px;
+    const Maps& maps = c->lane[c->last_lane].maps;
+    const uint8_t* base = (what == 0 ? maps.img : maps.S) + L.base + (size_t)pair * L.px;
     CU(c, cudaMemcpy(out, base, (size_t)L.px, cudaMemcpyDeviceToHost));
     if (dims) { dims[0] = L.w; dims[1] = L.h; }
     return MFK_OK;
@@ -679,8 +755,8 @@ int mfk_debug_layer(mfk_ctx* c, int what, int layer, int pair, uint8_t* out, int
 int mfk_debug_counters(mfk_ctx* c, uint32_t out[8]) {
     if (!c || !out) return MFK_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->stream));
-    CU(c, cudaMemcpy(out, c->cb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
+    CU(c, cudaMemcpy(out, c->counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return MFK_OK;
 }
 
@@ -688,11 +764,12 @@ int mfk_debug_keypoints(mfk_ctx* c, int pair, float* out, int cap, int* n) {
     if (!c || !n) return fail(c, MFK_ERR_ARG, "bad argument to mfk_debug_keypoints");
     if (!c->have_last || pair < 0 || pair >= c->last.F) return fail(c, MFK_ERR_STATE, "no such pair in the last batch");
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->stream));
+    { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
     const Geom& g = c->last;
+    const CandBuf& cb = c->lane[c->last_lane].cb;
     uint32_t range[2];
-    CU(c, cudaMemcpy(&range[0], c->cb.row_count + (size_t)pair * g.rows, 4, cudaMemcpyDeviceToHost));
-    CU(c, cudaMemcpy(&range[1], c->cb.row_count + (size_t)(pair + 1) * g.rows, 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(&range[0], cb.row_count + (size_t)pair * g.rows, 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(&range[1], cb.row_count + (size_t)(pair + 1) * g.rows, 4, cudaMemcpyDeviceToHost));
     range[0] = std::min<uint32_t>(range[0], (uint32_t)g.cand_cap);
     range[1] = std::min<uint32_t>(range[1], (uint32_t)g.cand_cap);
     const size_t m = range[1] - range[0];
@@ -700,12 +777,12 @@ int mfk_debug_keypoints(mfk_ctx* c, int pair, float* out, int cap, int* n) {
     std::vector<uint32_t> meta(m);
     std::vector<float> kx(m), ky(m), ks(m), kr(m);
     if (m) {
-        CU(c, cudaMemcpy(flags.data(), c->cb.flags + range[0], m, cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(meta.data(), c->cb.meta + range[0], m * 4, cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(kx.data(), c->cb.kx + range[0], m * 4, cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(ky.data(), c->cb.ky + range[0], m * 4, cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(ks.data(), c->cb.ksize + range[0], m * 4, cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(kr.data(), c->cb.kresp + range[0], m * 4, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(flags.data(), cb.flags + range[0], m, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(meta.data(), cb.meta + range[0], m * 4, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(kx.data(), cb.kx + range[0], m * 4, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(ky.data(), cb.ky + range[0], m * 4, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(ks.data(), cb.ksize + range[0], m * 4, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(kr.data(), cb.kresp + range[0], m * 4, cudaMemcpyDeviceToHost));
     }
     int count = 0;
     for (size_t i = 0; i < m; i++) {

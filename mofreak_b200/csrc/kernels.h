@@ -32,8 +32,9 @@ struct CandBuf {                  // ordered candidate list of the batch + per-c
     uint32_t* row_src;            // [cand_cap] candidate index of the batch's r-th output row
     uint32_t* pend_count;         // [F*6] tie candidates per (pair, layer), appended by phase A
     uint32_t* pend_list;          // [F*6][PEND_CAP] their candidate indices (unordered)
-    uint32_t* counters;           // [0] overflow flags (1 candidates, 2 rows), [1] rows accumulated so far,
-                                  // [2] pairs accumulated so far, [3] live candidate count of the batch
+    uint32_t* counters;           // shared by all batches: [0] overflow flags (1 candidates, 2 rows), [1] rows accumulated
+                                  // so far, [2] pairs accumulated so far, [3] live candidates of the last batch (copy)
+    uint32_t* live;               // [0] live candidate count of THIS batch (per buffer set)
 };
 
 enum { PEND_CAP = 2048 };         // per (pair, layer); beyond it phase B falls back to an ordered sweep

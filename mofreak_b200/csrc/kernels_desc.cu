@@ -81,7 +81,7 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
     __shared__ WarpScratch scratch[DW];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpScratch& ws = scratch[wib];
-    const uint32_t n_rows = cb.keep_scan[cb.counters[3]];
+    const uint32_t n_rows = cb.keep_scan[cb.live[0]];
     const uint32_t rows_base = cb.counters[1];
     const int W1 = g.W + 1;
     const size_t ipx = (size_t)W1 * (g.H + 1);

@@ -217,7 +217,7 @@ void launch_phase_b(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTa
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_keep_flags(Geom g, CandBuf cb) {
     const uint32_t n = min(cb.row_count[g.F * g.rows], (uint32_t)g.cand_cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0) cb.counters[3] = n;                       // live length for the scan
+    if (blockIdx.x == 0 && threadIdx.x == 0) cb.live[0] = n;                       // live length for the scan
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         cb.keep_scan[i] = (cb.flags[i] & ST_KEEP) ? 1u : 0u;
 }
@@ -233,7 +233,7 @@ namespace mfk {
 // after the scan of the keep flags: row r of the batch comes from candidate row_src[r]; rows of pair f are the
 // kept candidates between the pair's first and one-past-last candidate
 __global__ void k_scatter_rows(Geom g, CandBuf cb, uint32_t* __restrict__ pair_rows) {
-    const uint32_t n = cb.counters[3];
+    const uint32_t n = cb.live[0];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     for (uint32_t i = tid; i < n; i += nthreads)
         if (cb.flags[i] & ST_KEEP) cb.row_src[cb.keep_scan[i]] = i;
@@ -248,11 +248,12 @@ void launch_scatter_rows(cudaStream_t st, const Geom& g, CandBuf cb, uint32_t* p
 }
 
 __global__ void k_advance(Geom g, CandBuf cb) {
-    const uint32_t rows = cb.keep_scan[cb.counters[3]];
+    const uint32_t rows = cb.keep_scan[cb.live[0]];
     const uint32_t have = cb.counters[1];
     if (have + rows > (uint32_t)g.row_cap) { cb.counters[0] |= 2u; cb.counters[1] = (uint32_t)g.row_cap; }
     else cb.counters[1] = have + rows;
     cb.counters[2] += (uint32_t)g.F;
+    cb.counters[3] = cb.live[0];
 }
 
 void launch_advance(cudaStream_t st, const Geom& g, CandBuf cb) { k_advance<<<1, 1, 0, st>>>(g, cb); }
