@@ -140,6 +140,9 @@ int  mfk_timer_stop(mfk_ctx* ctx, float* elapsed_ms);   /* syncs */
 typedef struct mfk_prof_entry { const char* name; uint32_t launches; float total_ms; } mfk_prof_entry;
 int  mfk_profile_enable(mfk_ctx* ctx, int enable);
 int  mfk_profile_read(mfk_ctx* ctx, mfk_prof_entry* entries, int cap, int* n_entries);
+/* serial != 0: consecutive launch sequences no longer overlap (one buffer set, the integral image on the main stream).
+ * Throughput runs leave this off; the per-kernel accounting of mfk_profile_* is only a kernel's own time when it is on. */
+int  mfk_set_serial(mfk_ctx* ctx, int serial);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t mfk_launch_count(const mfk_ctx* ctx);
 

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mfk_extract_pairs", "mfk_fetch_rows", "mfk_rows_device", "mfk_reset_rows", "mfk_extract_clip", "mfk_mip_describe",
     "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram",
     "mfk_allreduce_counts", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read",
-    "mfk_launch_count", "mfk_debug_layer", "mfk_debug_keypoints", "mfk_debug_counters", "mfk_synth_clip", "mfk_freak_scale_index", "mfk_version",
+    "mfk_set_serial", "mfk_launch_count", "mfk_debug_layer", "mfk_debug_keypoints", "mfk_debug_counters", "mfk_synth_clip", "mfk_freak_scale_index", "mfk_version",
 ]
 
 
@@ -75,6 +75,7 @@ def lib():
     L.mfk_timer_stop.argtypes = [p, C.POINTER(C.c_float)]
     L.mfk_profile_enable.argtypes = [p, C.c_int]
     L.mfk_profile_read.argtypes = [p, C.POINTER(_ProfEntry), C.c_int, C.POINTER(C.c_int)]
+    L.mfk_set_serial.argtypes = [p, C.c_int]
     L.mfk_launch_count.argtypes = [p]; L.mfk_launch_count.restype = C.c_uint64
     L.mfk_debug_layer.argtypes = [p, C.c_int, C.c_int, C.c_int, u8p, C.POINTER(C.c_int)]
     L.mfk_debug_keypoints.argtypes = [p, C.c_int, f32p, C.c_int, C.POINTER(C.c_int)]
@@ -238,6 +239,9 @@ class Context:
         n = C.c_int()
         self._check(self._L.mfk_profile_read(self._h, ent, 16, C.byref(n)))
         return {ent[i].name.decode(): (ent[i].launches, ent[i].total_ms) for i in range(n.value)}
+
+    def set_serial(self, on=True):
+        self._check(self._L.mfk_set_serial(self._h, 1 if on else 0))
 
     def launch_count(self):
         return int(self._L.mfk_launch_count(self._h))

@@ -67,6 +67,7 @@ struct mfk_ctx {
     };
     Lane lane[2];
     int n_lanes = 2;
+    bool serial = false;
     uint64_t batches = 0;
     int last_lane = 0;
     uint32_t* counters = nullptr;
@@ -234,10 +235,14 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
     CU(c, cudaMemsetAsync(L.cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
     { Span s(c, P_ABSDIFF, 1, st);   launch_absdiff(st, g, c->store, c->store_frames, pl, L.maps.img); }
     // the integral image only needs layer 0: fork it onto the side stream, join before the descriptor kernel
-    CU(c, cudaEventRecord(L.aux_fork, st));
-    CU(c, cudaStreamWaitEvent(L.aux_stream, L.aux_fork, 0));
-    { Span s(c, P_INTEGRAL, 2, L.aux_stream);  launch_integral(L.aux_stream, g, L.maps.img, L.integral); }
-    CU(c, cudaEventRecord(L.aux_join, L.aux_stream));
+    if (c->serial) {
+        Span s(c, P_INTEGRAL, 2, st);  launch_integral(st, g, L.maps.img, L.integral);
+    } else {
+        CU(c, cudaEventRecord(L.aux_fork, st));
+        CU(c, cudaStreamWaitEvent(L.aux_stream, L.aux_fork, 0));
+        { Span s(c, P_INTEGRAL, 2, L.aux_stream);  launch_integral(L.aux_stream, g, L.maps.img, L.integral); }
+        CU(c, cudaEventRecord(L.aux_join, L.aux_stream));
+    }
     { Span s(c, P_PYRAMID, 5, st);   launch_pyramid(st, g, L.maps.img); }
     { Span s(c, P_SCORES, 1, st);    launch_scores(st, g, L.maps.img, L.maps.S, L.cb.row_count); }
     { Span s(c, P_SCAN, 3, st);      launch_exclusive_scan(st, L.cb.row_count, F * g.rows, nullptr, L.scan_scratch); }
@@ -251,7 +256,7 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
       launch_exclusive_scan(st, L.cb.keep_scan, c->cand_cap, L.cb.live, L.scan_scratch);
       launch_scatter_rows(st, g, L.cb, c->pair_rows);
     }
-    CU(c, cudaStreamWaitEvent(st, L.aux_join, 0));
+    if (!c->serial) CU(c, cudaStreamWaitEvent(st, L.aux_join, 0));
     { Span s(c, P_DESCRIBE, 2, st);
       launch_describe(st, g, c->store, c->store_frames, pl, L.maps.img, L.integral, L.cb, c->tb, c->rows_buf);
       launch_advance(st, g, L.cb);
@@ -732,6 +737,15 @@ int mfk_profile_read(mfk_ctx* c, mfk_prof_entry* entries, int cap, int* n_entrie
         n++;
     }
     *n_entries = n;
+    return MFK_OK;
+}
+
+int mfk_set_serial(mfk_ctx* c, int serial) {
+    if (!c) return MFK_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
+    c->serial = serial != 0;
+    c->n_lanes = c->serial ? 1 : 2;
     return MFK_OK;
 }
 
