@@ -247,6 +247,16 @@ def run_ours(args):
     ctx.set_serial(False)
     barrier()
 
+    # ---- bag-of-words assignment of the step's rows against a 600-word codebook (BASELINE configs[2] shape), on the device ----
+    rng = np.random.default_rng(7)
+    ctx.bow_set_codebook(rng.integers(0, 256, (600, 16), dtype=np.uint8))
+    step_resident(); ctx.sync()
+    ctx.bow_histogram_rows()
+    ctx.timer_start()
+    for _ in range(max(3, args.steps)):
+        ctx.bow_histogram_rows()
+    ms_bow = ctx.timer_stop() / max(3, args.steps)
+
     # ---- end to end: host buffers in, host rows out, copies inside the timed region ----
     # chunks of whole streams: the upload of chunk k+1 (copy stream) overlaps the kernels of chunk k
     chunk_streams = max(1, min(STREAMS, MAX_PAIRS // PAIRS_PER_STREAM))
@@ -322,6 +332,10 @@ def run_ours(args):
             "kernel_accounting": "CUDA events per kernel family over %d serialised steps of the same run (%.2f ms/step serialised vs "
                                  "%.2f ms/step with two launch sequences overlapping)" % (args.steps, ms_serial / args.steps, ms_res / args.steps),
             "clocks": clocks,
+            "bow": {"codebook_words": 600, "descriptors_per_call": int(n_rows_step), "ms_per_call": ms_bow,
+                    "descriptors_per_sec": n_rows_step / (ms_bow / 1e3), "popc64_per_sec": n_rows_step * 1200 / (ms_bow / 1e3),
+                    "note": "mfk_bow_histogram_rows on the device-resident rows of one step incl. the 2.4 KB count read-back; "
+                            "integer-pipe bound (2 XOR + 2 POPC.64 per codeword), HBM traffic 32 B per descriptor"},
         }
         if cpu:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"]}

@@ -130,30 +130,41 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
         *reinterpret_cast<uint4*>(&tile[r][4 * k]) = q;
     }
     __syncthreads();
-    uint8_t* S = S_all + L.base + (size_t)f * L.px;
+    // ---- score: per-thread invariants are hoisted so that a pixel costs its 17 shared loads, the 40 packed
+    // min/max and a handful of other instructions (the kernel sits on the ALU pipe) ----
+    const uint32_t* t0 = &tile[threadIdx.y + 3][threadIdx.x + 4];      // centre of this thread's first pixel
+    const int xa = x0 + threadIdx.x, ya = y0 + threadIdx.y;
+    uint8_t* Sp = S_all + L.base + (size_t)f * L.px + (size_t)ya * w + xa;
+    bool in_x[SC_TW / 32], st_x[SC_TW / 32];
+#pragma unroll
+    for (int jx = 0; jx < SC_TW / 32; jx++) {
+        const int x = xa + 32 * jx;
+        in_x[jx] = x >= 3 && x < w - 3;
+        st_x[jx] = x < w;
+    }
+    uint32_t* rc = row_count + (size_t)f * g.rows + L.row0 + ya;
 #pragma unroll
     for (int jy = 0; jy < SC_TH / 8; jy++) {
-        const int ly = threadIdx.y + 8 * jy;
-        const int y = y0 + ly, cy = ly + 3;
+        const int y = ya + 8 * jy;
+        const bool in_y = y >= 3 && y < h - 3, st_y = y < h;
         unsigned row_hits = 0;
 #pragma unroll
         for (int jx = 0; jx < SC_TW / 32; jx++) {
-            const int lx = threadIdx.x + 32 * jx;
-            const int x = x0 + lx, cx = lx + 4;
+            const uint32_t* c = t0 + (8 * jy) * SC_SW + 32 * jx;
             // ring in circle order (oast9_16.h:214-232)
             uint32_t r[16];
-            r[0] = tile[cy][cx - 3];      r[1] = tile[cy - 1][cx - 3];  r[2] = tile[cy - 2][cx - 2];  r[3] = tile[cy - 3][cx - 1];
-            r[4] = tile[cy - 3][cx];      r[5] = tile[cy - 3][cx + 1];  r[6] = tile[cy - 2][cx + 2];  r[7] = tile[cy - 1][cx + 3];
-            r[8] = tile[cy][cx + 3];      r[9] = tile[cy + 1][cx + 3];  r[10] = tile[cy + 2][cx + 2]; r[11] = tile[cy + 3][cx + 1];
-            r[12] = tile[cy + 3][cx];     r[13] = tile[cy + 3][cx - 1]; r[14] = tile[cy + 2][cx - 2]; r[15] = tile[cy + 1][cx - 3];
-            int s = oast_score_packed(r, tile[cy][cx]);
-            const bool inside = (x >= 3 && y >= 3 && x < w - 3 && y < h - 3);
-            if (!inside) s = 0;
-            if (x < w && y < h) S[y * w + x] = (uint8_t)s;
+            r[0] = c[-3];                 r[1] = c[-SC_SW - 3];         r[2] = c[-2 * SC_SW - 2];     r[3] = c[-3 * SC_SW - 1];
+            r[4] = c[-3 * SC_SW];         r[5] = c[-3 * SC_SW + 1];     r[6] = c[-2 * SC_SW + 2];     r[7] = c[-SC_SW + 3];
+            r[8] = c[3];                  r[9] = c[SC_SW + 3];          r[10] = c[2 * SC_SW + 2];     r[11] = c[3 * SC_SW + 1];
+            r[12] = c[3 * SC_SW];         r[13] = c[3 * SC_SW - 1];     r[14] = c[2 * SC_SW - 2];     r[15] = c[SC_SW - 3];
+            int sc = oast_score_packed(r, c[0]);
+            const bool inside = in_y && in_x[jx];
+            sc = inside ? sc : 0;
+            if (st_y && st_x[jx]) Sp[(8 * jy) * w + 32 * jx] = (uint8_t)sc;
             // one warp = one tile row segment: count its hits with a ballot
-            row_hits += __popc(__ballot_sync(0xffffffffu, inside && s >= BRISK_THRESHOLD));
+            row_hits += __popc(__ballot_sync(0xffffffffu, sc >= BRISK_THRESHOLD));
         }
-        if (threadIdx.x == 0 && row_hits && y < h) atomicAdd(&row_count[(size_t)f * g.rows + L.row0 + y], row_hits);
+        if (threadIdx.x == 0 && row_hits) atomicAdd(rc + 8 * jy, row_hits);
     }
 }
 

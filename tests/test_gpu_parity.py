@@ -232,6 +232,19 @@ def test_full_size_properties_kth_batch():
     assert per.sum() == len(rows)
 
 
+def test_serial_and_pipelined_launch_sequences_agree(orc):
+    """Consecutive launch sequences alternate between two buffer sets on two streams; the rows must not depend on it."""
+    clip = mofreak_b200.synth_clip(320, 240, 30, 77)
+    want = orc.extract_clip(clip)
+    with mofreak_b200.Context(320, 240, 30, 4) as ctx:          # 25 pairs -> 7 launch sequences
+        a = ctx.extract_clip(clip)
+        ctx.set_serial(True)
+        b = ctx.extract_clip(clip)
+        ctx.set_serial(False)
+        c = ctx.extract_clip(clip)
+    assert util.rows_equal(a, want) and util.rows_equal(b, want) and util.rows_equal(c, want)
+
+
 def test_timer_and_profile_hooks():
     clip = mofreak_b200.synth_clip(160, 120, 9, 301)
     with mofreak_b200.Context(160, 120, 16, 4) as ctx:
