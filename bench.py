@@ -260,10 +260,17 @@ def run_ours(args):
     # ---- end to end: host buffers in, host rows out, copies inside the timed region ----
     # chunks of whole streams: the upload of chunk k+1 (copy stream) overlaps the kernels of chunk k
     chunk_streams = max(1, min(STREAMS, MAX_PAIRS // PAIRS_PER_STREAM))
-    chunks = []
-    for s0 in range(0, STREAMS, chunk_streams):
-        s1 = min(STREAMS, s0 + chunk_streams)
+    # a short first chunk keeps the one upload nothing can hide behind small
+    sizes, left = [], STREAMS
+    if STREAMS > chunk_streams >= 2:
+        sizes += [1, chunk_streams - 1]; left -= chunk_streams
+    while left > 0:
+        sizes.append(min(chunk_streams, left)); left -= sizes[-1]
+    chunks, s0 = [], 0
+    for n_s in sizes:
+        s1 = s0 + n_s
         chunks.append((s0 * FRAMES_PER_STREAM, (s1 - s0) * FRAMES_PER_STREAM, slice(s0 * PAIRS_PER_STREAM, s1 * PAIRS_PER_STREAM)))
+        s0 = s1
     frame_bytes = W * H
 
     def step_e2e():
