@@ -59,6 +59,7 @@ struct mfk_ctx {
     struct Lane {
         Maps maps{};
         int32_t* integral = nullptr;
+        int32_t* integral_left = nullptr;     // per image row: sums left of each 32-column strip
         CandBuf cb{};
         uint32_t* scan_scratch = nullptr;
         cudaStream_t stream = nullptr, aux_stream = nullptr;
@@ -236,11 +237,11 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
     { Span s(c, P_ABSDIFF, 1, st);   launch_absdiff(st, g, c->store, c->store_frames, pl, L.maps.img); }
     // the integral image only needs layer 0: fork it onto the side stream, join before the descriptor kernel
     if (c->serial) {
-        Span s(c, P_INTEGRAL, 2, st);  launch_integral(st, g, L.maps.img, L.integral);
+        Span s(c, P_INTEGRAL, 2, st);  launch_integral(st, g, L.maps.img, L.integral, L.integral_left);
     } else {
         CU(c, cudaEventRecord(L.aux_fork, st));
         CU(c, cudaStreamWaitEvent(L.aux_stream, L.aux_fork, 0));
-        { Span s(c, P_INTEGRAL, 2, L.aux_stream);  launch_integral(L.aux_stream, g, L.maps.img, L.integral); }
+        { Span s(c, P_INTEGRAL, 2, L.aux_stream);  launch_integral(L.aux_stream, g, L.maps.img, L.integral, L.integral_left); }
         CU(c, cudaEventRecord(L.aux_join, L.aux_stream));
     }
     { Span s(c, P_PYRAMID, 5, st);   launch_pyramid(st, g, L.maps.img); }
@@ -277,7 +278,7 @@ void destroy(mfk_ctx* c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->store);
     for (auto& L : c->lane) {
-        cudaFree(L.maps.img); cudaFree(L.maps.S); cudaFree(L.maps.seen); cudaFree(L.maps.status); cudaFree(L.integral);
+        cudaFree(L.maps.img); cudaFree(L.maps.S); cudaFree(L.maps.seen); cudaFree(L.maps.status); cudaFree(L.integral); cudaFree(L.integral_left);
         cudaFree(L.cb.row_count); cudaFree(L.cb.xy); cudaFree(L.cb.meta); cudaFree(L.cb.kx); cudaFree(L.cb.ky); cudaFree(L.cb.ksize);
         cudaFree(L.cb.kresp); cudaFree(L.cb.flags); cudaFree(L.cb.scale_idx); cudaFree(L.cb.keep_scan); cudaFree(L.cb.row_src);
         cudaFree(L.cb.pend_count); cudaFree(L.cb.pend_list); cudaFree(L.cb.live); cudaFree(L.scan_scratch);
@@ -386,6 +387,7 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
         CUC(dalloc(&L.maps.seen, F * c->pyr_px + slack));
         CUC(dalloc(&L.maps.status, F * c->pyr_px + slack));
         CUC(dalloc(&L.integral, F * (size_t)(width + 1) * (height + 1)));
+        CUC(dalloc(&L.integral_left, F * (size_t)height * ((width + 31) / 32)));
         CUC(dalloc(&L.cb.row_count, F * c->rows + 2));
         CUC(dalloc(&L.cb.xy, cand_cap)); CUC(dalloc(&L.cb.meta, cand_cap));
         CUC(dalloc(&L.cb.kx, cand_cap)); CUC(dalloc(&L.cb.ky, cand_cap));

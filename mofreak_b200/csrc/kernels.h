@@ -52,7 +52,8 @@ void launch_absdiff(cudaStream_t, const Geom&, const uint8_t* store, int store_f
 void launch_pyramid(cudaStream_t, const Geom&, uint8_t* img);                                  // layers 1..5
 void launch_scores(cudaStream_t, const Geom&, const uint8_t* img, uint8_t* S, uint32_t* row_count);
 void launch_fill_candidates(cudaStream_t, const Geom&, const uint8_t* S, CandBuf);
-void launch_integral(cudaStream_t, const Geom&, const uint8_t* img /*layer 0*/, int32_t* integral);
+void launch_integral(cudaStream_t, const Geom&, const uint8_t* img /*layer 0*/, int32_t* integral,
+                     int32_t* left /*F*H*ceil(W/32) scratch*/);
 // --- scans --------------------------------------------------------------------------------------------
 // exclusive scan of data[0..n) in place, data[n] = total; n is a host upper bound, *d_n (optional
 // device value <= n) the live length; scratch holds ceil(n/2048)+1 words

@@ -248,49 +248,90 @@ void launch_fill_candidates(cudaStream_t st, const Geom& g, const uint8_t* S, Ca
 // ---------------------------------------------------------------------------------------------------
 // integral image of the difference frame, int32 (H+1) x (W+1) with a zero top row / left column
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_integral_rows(const uint8_t* __restrict__ img, int32_t* __restrict__ integral, int W, int H, int F) {
+// Two passes over the image, one write of the integral (the classic row-scan + column-scan writes and re-reads it):
+//   k_integral_left    per image row: left[y][s] = sum of the pixels left of 32-column strip s
+//   k_integral_strips  one warp per (pair, strip) walks down the rows keeping, per lane, the running column sum of the
+//                      in-strip row prefixes, and per warp the running sum of left[y][s]; their sum is the integral.
+constexpr int IG_STRIP = 32;
+
+__global__ void k_integral_left(const uint8_t* __restrict__ img, int32_t* __restrict__ left, int W, int H, int F, int strips) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= F * (H + 1)) return;
-    const int f = warp / (H + 1), yy = warp - f * (H + 1);        // yy = output row
-    int32_t* out = integral + ((size_t)f * (H + 1) + yy) * (W + 1);
-    if (yy == 0) {
-        for (int x = lane; x <= W; x += 32) out[x] = 0;
-        return;
-    }
-    const uint8_t* row = img + (size_t)f * W * H + (size_t)(yy - 1) * W;
-    if (lane == 0) out[0] = 0;
+    if (warp >= F * H) return;
+    const uint8_t* row = img + (size_t)warp * W;                       // rows of all pairs are contiguous (layer 0 block)
+    int32_t* out = left + (size_t)warp * strips;
     int carry = 0;
-    for (int x0 = 0; x0 < W; x0 += 32) {
-        const int x = x0 + lane;
-        int v = x < W ? row[x] : 0;
+    for (int s0 = 0; s0 < strips; s0 += 32) {
+        const int s = s0 + lane;
+        int sum = 0;
+        if (s < strips) {
+            const int x0 = s * IG_STRIP;
+#pragma unroll
+            for (int k = 0; k < IG_STRIP; k += 4) {
+                if (x0 + k + 4 <= W) sum = (int)__dp4a(load4(row + x0 + k), 0x01010101u, (unsigned)sum);
+                else for (int j = 0; j < 4; j++) if (x0 + k + j < W) sum += row[x0 + k + j];
+            }
+        }
+        int incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= d) v += n;
+            const int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
         }
-        if (x < W) out[x + 1] = carry + v;
-        carry += __shfl_sync(0xffffffffu, v, 31);
+        if (s < strips) out[s] = carry + incl - sum;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
-__global__ void k_integral_cols(int32_t* __restrict__ integral, int W, int H, int F) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= F * (W + 1)) return;
-    const int f = t / (W + 1), x = t - f * (W + 1);
-    int32_t* col = integral + (size_t)f * (H + 1) * (W + 1) + x;
-    int acc = 0;
-    for (int y = 1; y <= H; y++) {
-        acc += col[(size_t)y * (W + 1)];
-        col[(size_t)y * (W + 1)] = acc;
+constexpr int IG_AHEAD = 8;       // rows fetched ahead of the dependent scan chain
+
+__global__ void k_integral_strips(const uint8_t* __restrict__ img, const int32_t* __restrict__ left, int32_t* __restrict__ integral,
+                                  int W, int H, int F, int strips) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= F * strips) return;
+    const int f = warp / strips, s = warp - f * strips;
+    const int x = s * IG_STRIP + lane;
+    const bool live = x < W;
+    const uint8_t* col = img + (size_t)f * W * H + (live ? x : 0);
+    const int32_t* lf = left + (size_t)f * H * strips + s;
+    int32_t* out = integral + (size_t)f * (H + 1) * (W + 1);
+    if (live) out[x + 1] = 0;                                            // zero top row
+    if (s == 0 && lane == 0) out[0] = 0;
+    int col_acc = 0, left_acc = 0;
+    for (int y0 = 0; y0 < H; y0 += IG_AHEAD) {
+        int px[IG_AHEAD], lv[IG_AHEAD];
+#pragma unroll
+        for (int k = 0; k < IG_AHEAD; k++) {
+            const int y = y0 + k;
+            px[k] = (live && y < H) ? col[(size_t)y * W] : 0;
+            lv[k] = (y < H) ? lf[(size_t)y * strips] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < IG_AHEAD; k++) {
+            const int y = y0 + k;
+            if (y >= H) break;
+            int incl = px[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += n;
+            }
+            col_acc += incl;
+            left_acc += lv[k];
+            int32_t* o = out + (size_t)(y + 1) * (W + 1);
+            if (live) o[x + 1] = col_acc + left_acc;
+            if (s == 0 && lane == 0) o[0] = 0;                           // zero left column
+        }
     }
 }
 
-void launch_integral(cudaStream_t st, const Geom& g, const uint8_t* img, int32_t* integral) {
-    const int warps = g.F * (g.H + 1);
-    k_integral_rows<<<(warps * 32 + 255) / 256, 256, 0, st>>>(img, integral, g.W, g.H, g.F);
-    const int threads = g.F * (g.W + 1);
-    k_integral_cols<<<(threads + 127) / 128, 128, 0, st>>>(integral, g.W, g.H, g.F);
+void launch_integral(cudaStream_t st, const Geom& g, const uint8_t* img, int32_t* integral, int32_t* left) {
+    const int strips = (g.W + IG_STRIP - 1) / IG_STRIP;
+    const int warps1 = g.F * g.H;
+    k_integral_left<<<(warps1 * 32 + 255) / 256, 256, 0, st>>>(img, left, g.W, g.H, g.F, strips);
+    const int warps2 = g.F * strips;
+    k_integral_strips<<<(warps2 * 32 + 127) / 128, 128, 0, st>>>(img, left, integral, g.W, g.H, g.F, strips);
 }
 
 // ---------------------------------------------------------------------------------------------------
