@@ -234,6 +234,7 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
     CU(c, cudaMemsetAsync(L.cb.row_count, 0, ((size_t)F * g.rows + 1) * sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(L.maps.seen, 0, (size_t)F * g.pyr_px, st));
     CU(c, cudaMemsetAsync(L.cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
+    CU(c, cudaMemsetAsync(L.cb.q_count, 0, 4 * sizeof(uint32_t), st));
     { Span s(c, P_ABSDIFF, 1, st);   launch_absdiff(st, g, c->store, c->store_frames, pl, L.maps.img); }
     // the integral image only needs layer 0: fork it onto the side stream, join before the descriptor kernel
     if (c->serial) {
@@ -248,7 +249,7 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
     { Span s(c, P_SCORES, 1, st);    launch_scores(st, g, L.maps.img, L.maps.S, L.cb.row_count); }
     { Span s(c, P_SCAN, 3, st);      launch_exclusive_scan(st, L.cb.row_count, F * g.rows, nullptr, L.scan_scratch); }
     { Span s(c, P_FILL, 1, st);      launch_fill_candidates(st, g, L.maps.S, L.cb); }
-    { Span s(c, P_PHASE_A, 1, st);   launch_phase_a(st, g, L.maps, L.cb, c->tb); }
+    { Span s(c, P_PHASE_A, 4, st);   launch_phase_a(st, g, L.maps, L.cb, c->tb); }
     { Span s(c, P_PHASE_B, 1, st);   launch_phase_b(st, g, L.maps, L.cb, c->tb); }
     // from here on the shared row accumulation is touched: wait until the previous batch has advanced it
     if (c->batches > 0 && c->last_lane != li) CU(c, cudaStreamWaitEvent(st, P.advanced, 0));
@@ -281,7 +282,8 @@ void destroy(mfk_ctx* c) {
         cudaFree(L.maps.img); cudaFree(L.maps.S); cudaFree(L.maps.seen); cudaFree(L.maps.status); cudaFree(L.integral); cudaFree(L.integral_left);
         cudaFree(L.cb.row_count); cudaFree(L.cb.xy); cudaFree(L.cb.meta); cudaFree(L.cb.kx); cudaFree(L.cb.ky); cudaFree(L.cb.ksize);
         cudaFree(L.cb.kresp); cudaFree(L.cb.flags); cudaFree(L.cb.scale_idx); cudaFree(L.cb.keep_scan); cudaFree(L.cb.row_src);
-        cudaFree(L.cb.pend_count); cudaFree(L.cb.pend_list); cudaFree(L.cb.live); cudaFree(L.scan_scratch);
+        cudaFree(L.cb.pend_count); cudaFree(L.cb.pend_list); cudaFree(L.cb.live);
+        cudaFree(L.cb.q_count); cudaFree(L.cb.q0); cudaFree(L.cb.q1); cudaFree(L.cb.q2); cudaFree(L.cb.q1_up); cudaFree(L.cb.q2_scan); cudaFree(L.scan_scratch);
         for (cudaEvent_t e : {L.aux_fork, L.aux_join, L.advanced, L.done}) if (e) cudaEventDestroy(e);
         if (L.aux_stream) cudaStreamDestroy(L.aux_stream);
         if (L.stream) cudaStreamDestroy(L.stream);
@@ -396,6 +398,10 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
         CUC(dalloc(&L.cb.keep_scan, cand_cap + 2)); CUC(dalloc(&L.cb.row_src, cand_cap));
         CUC(dalloc(&L.cb.pend_count, F * N_LAYERS));
         CUC(dalloc(&L.cb.pend_list, F * N_LAYERS * PEND_CAP));
+        L.cb.q_cap = (uint32_t)std::max<size_t>(cand_cap / 4, 4096);
+        CUC(dalloc(&L.cb.q_count, 4));
+        CUC(dalloc(&L.cb.q0, L.cb.q_cap)); CUC(dalloc(&L.cb.q1, L.cb.q_cap)); CUC(dalloc(&L.cb.q2, L.cb.q_cap));
+        CUC(dalloc(&L.cb.q1_up, (size_t)3 * L.cb.q_cap)); CUC(dalloc(&L.cb.q2_scan, (size_t)6 * L.cb.q_cap));
         CUC(dalloc(&L.cb.live, 2));
         CUC(cudaMemset(L.cb.live, 0, 2 * sizeof(uint32_t)));
         L.cb.counters = c->counters;

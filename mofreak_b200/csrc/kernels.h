@@ -32,6 +32,12 @@ struct CandBuf {                  // ordered candidate list of the batch + per-c
     uint32_t* row_src;            // [cand_cap] candidate index of the batch's r-th output row
     uint32_t* pend_count;         // [F*6] tie candidates per (pair, layer), appended by phase A
     uint32_t* pend_list;          // [F*6][PEND_CAP] their candidate indices (unordered)
+    // phase A work queues (unordered; device-wide re-packing between the steps of phase A)
+    uint32_t* q_count;            // [3] entries in q0 / q1 / q2
+    uint32_t* q0;                 // [q_cap] candidates that passed the 8-neighbour test without a tie
+    uint32_t* q1; float* q1_up;   // [q_cap] after the scan above, with its (max, dx, dy)
+    uint32_t* q2; float* q2_scan; // [q_cap] after the scan below, with (up.max, up.dx, up.dy, dn.max, dn.dx, dn.dy)
+    uint32_t q_cap;
     uint32_t* counters;           // shared by all batches: [0] overflow flags (1 candidates, 2 rows), [1] rows accumulated
                                   // so far, [2] pairs accumulated so far, [3] live candidates of the last batch (copy)
     uint32_t* live;               // [0] live candidate count of THIS batch (per buffer set)

@@ -19,29 +19,32 @@ namespace mfk {
 // ---------------------------------------------------------------------------------------------------
 // phase A
 // ---------------------------------------------------------------------------------------------------
-// Four steps per chunk of PA_CHUNK candidates, re-packing the survivors between them so that every expensive step
-// runs on (nearly) full warps:
-//   1. every thread tests PA_ITEMS candidates against their 8 neighbours (3 aligned row loads each); losers are
-//      final, candidates with an equal neighbour go to the pair's tie list, the rest to a shared-memory queue;
-//   2. scan of the layer above (stage_above) for the queue; 3. scan of the layer below (stage_below) for what is left;
-//   4. refinement and keypoint record (stage_emit) for the survivors.
-constexpr int PA_THREADS = 128, PA_ITEMS = 4, PA_CHUNK = PA_THREADS * PA_ITEMS;
+// Four kernels, re-packing the survivors device-wide between them so that every expensive step runs on full warps
+// and no warp waits at a block barrier for a slower one:
+//   k_pa_test   every candidate against its 8 neighbours (3 aligned row loads); losers are final, candidates with an
+//               equal neighbour go to their pair's tie list, the rest to queue 0;
+//   k_pa_above  scan of the layer above (stage_above) -> queue 1;   k_pa_below  scan of the layer below -> queue 2;
+//   k_pa_emit   refinement and keypoint record (stage_emit).
+// Queues are unordered (warp-aggregated atomic appends): candidates are independent of each other in phase A.
+constexpr int PA_THREADS = 128;
 
-struct PaItem { uint32_t c; Scan up; Scan dn; };
+// all 32 lanes must call; returns the slot for lanes with pred
+__device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (!m) return 0;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
 
-__global__ void __launch_bounds__(PA_THREADS) k_phase_a(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
-    __shared__ uint32_t queue0[PA_CHUNK];
-    __shared__ PaItem queue1[PA_CHUNK];
-    __shared__ uint32_t queue2[PA_CHUNK];       // indices into queue1
-    __shared__ int q_n[3];
+__global__ void __launch_bounds__(PA_THREADS) k_pa_test(const __grid_constant__ Geom g, Maps m, CandBuf cb) {
     const uint32_t n = min(cb.row_count[g.F * g.rows], (uint32_t)g.cand_cap);
-    for (uint32_t base = blockIdx.x * PA_CHUNK; base < n; base += gridDim.x * PA_CHUNK) {
-        if (threadIdx.x < 3) q_n[threadIdx.x] = 0;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < PA_ITEMS; k++) {
-            const uint32_t c = base + k * PA_THREADS + threadIdx.x;
-            if (c >= n) continue;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += gridDim.x * blockDim.x) {
+        bool pass = false;
+        if (c < n) {
             const uint32_t xy = cb.xy[c], meta = cb.meta[c];
             const int x = xy & 0xffff, y = xy >> 16, li = meta & 7, f = meta >> 3;
             const LayerGeom& L = g.L[li];
@@ -55,50 +58,83 @@ __global__ void __launch_bounds__(PA_THREADS) k_phase_a(const __grid_constant__ 
             const uint32_t m02 = __vmaxu4(m01, r1 & 0xff00ffu);                      // left and right neighbour
             const int mx = max(max((int)(m02 & 0xff), (int)((m02 >> 8) & 0xff)), (int)((m02 >> 16) & 0xff));
             uint8_t* status = m.status + off + y * L.w + x;
-            if (mx > c0) { *status = 0; cb.flags[c] = 0; continue; }
-            if (mx == c0) {
+            if (mx > c0) { *status = 0; cb.flags[c] = 0; }
+            else if (mx == c0) {
                 *status = ST_PENDING; cb.flags[c] = ST_PENDING;
                 const uint32_t slot = atomicAdd(&cb.pend_count[f * N_LAYERS + li], 1u);
                 if (slot < PEND_CAP) cb.pend_list[(size_t)(f * N_LAYERS + li) * PEND_CAP + slot] = c;
-                continue;
-            }
-            queue0[atomicAdd(&q_n[0], 1)] = c;
+            } else pass = true;
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < q_n[0]; i += PA_THREADS) {
-            const uint32_t c = queue0[i];
+        const uint32_t slot = warp_append(&cb.q_count[0], pass);
+        if (pass) { if (slot < cb.q_cap) cb.q0[slot] = c; else atomicOr(&cb.counters[0], 1u); }
+    }
+}
+
+__global__ void __launch_bounds__(PA_THREADS) k_pa_above(const __grid_constant__ Geom g, Maps m, CandBuf cb) {
+    const uint32_t n = min(cb.q_count[0], cb.q_cap);
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool pass = false;
+        uint32_t c = 0;
+        Scan up = neutral_scan();
+        if (i < n) {
+            c = cb.q0[i];
             const uint32_t xy = cb.xy[c], meta = cb.meta[c];
             PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
-            Scan up;
-            if (stage_above(pv, cb, meta & 7, xy & 0xffff, xy >> 16, c, up)) {
-                const int slot = atomicAdd(&q_n[1], 1);
-                queue1[slot].c = c; queue1[slot].up = up;
-            }
+            pass = stage_above(pv, cb, meta & 7, xy & 0xffff, xy >> 16, c, up);
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < q_n[1]; i += PA_THREADS) {
-            const uint32_t c = queue1[i].c;
+        const uint32_t slot = warp_append(&cb.q_count[1], pass);
+        if (pass) {
+            if (slot < cb.q_cap) { cb.q1[slot] = c; cb.q1_up[3 * (size_t)slot] = up.max; cb.q1_up[3 * (size_t)slot + 1] = up.dx; cb.q1_up[3 * (size_t)slot + 2] = up.dy; }
+            else atomicOr(&cb.counters[0], 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PA_THREADS) k_pa_below(const __grid_constant__ Geom g, Maps m, CandBuf cb) {
+    const uint32_t n = min(cb.q_count[1], cb.q_cap);
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool pass = false;
+        uint32_t c = 0;
+        Scan dn = neutral_scan();
+        if (i < n) {
+            c = cb.q1[i];
             const uint32_t xy = cb.xy[c], meta = cb.meta[c];
             PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
-            Scan dn;
-            if (stage_below(pv, cb, meta & 7, xy & 0xffff, xy >> 16, c, dn)) {
-                queue1[i].dn = dn;
-                queue2[atomicAdd(&q_n[2], 1)] = (uint32_t)i;
-            }
+            pass = stage_below(pv, cb, meta & 7, xy & 0xffff, xy >> 16, c, dn);
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < q_n[2]; i += PA_THREADS) {
-            const PaItem it = queue1[queue2[i]];
-            const uint32_t xy = cb.xy[it.c], meta = cb.meta[it.c];
-            PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
-            stage_emit(pv, cb, tb, meta & 7, xy & 0xffff, xy >> 16, it.c, it.up, it.dn);
+        const uint32_t slot = warp_append(&cb.q_count[2], pass);
+        if (pass) {
+            if (slot < cb.q_cap) {
+                cb.q2[slot] = c;
+                float* o = cb.q2_scan + 6 * (size_t)slot;
+                const float* u = cb.q1_up + 3 * (size_t)i;
+                o[0] = u[0]; o[1] = u[1]; o[2] = u[2]; o[3] = dn.max; o[4] = dn.dx; o[5] = dn.dy;
+            } else atomicOr(&cb.counters[0], 1u);
         }
-        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(PA_THREADS) k_pa_emit(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
+    const uint32_t n = min(cb.q_count[2], cb.q_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = cb.q2[i];
+        const float* o = cb.q2_scan + 6 * (size_t)i;
+        Scan up = neutral_scan(), dn = neutral_scan();
+        up.max = o[0]; up.dx = o[1]; up.dy = o[2]; dn.max = o[3]; dn.dx = o[4]; dn.dy = o[5];
+        const uint32_t xy = cb.xy[c], meta = cb.meta[c];
+        PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
+        stage_emit(pv, cb, tb, meta & 7, xy & 0xffff, xy >> 16, c, up, dn);
     }
 }
 
 void launch_phase_a(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTables tb) {
-    k_phase_a<<<148 * 8, PA_THREADS, 0, st>>>(g, m, cb, tb);
+    const int grid = 148 * 8;
+    k_pa_test<<<grid, PA_THREADS, 0, st>>>(g, m, cb);
+    k_pa_above<<<grid, PA_THREADS, 0, st>>>(g, m, cb);
+    k_pa_below<<<grid, PA_THREADS, 0, st>>>(g, m, cb);
+    k_pa_emit<<<grid, PA_THREADS, 0, st>>>(g, m, cb, tb);
 }
 
 // ---------------------------------------------------------------------------------------------------
