@@ -48,14 +48,18 @@ __device__ __forceinline__ void resize_roi_pair(WarpScratch& ws, const uint8_t* 
         __syncwarp();
         for (int o = lane; o < PATCH_PX; o += 32) {
             const int dy = o / PATCH, dx = o - dy * PATCH;
-            ws.cur[o] = (uint8_t)resize_px(ws.roi[0], ROI_MAX, s, ws.tap[dy], ws.tap[dx]);
-            ws.prev[o] = (uint8_t)resize_px(ws.roi[1], ROI_MAX, s, ws.tap[dy], ws.tap[dx]);
+            int va, vb;
+            resize_px_pair(ws.roi[0], ws.roi[1], ROI_MAX, s, ws.tap[dy], ws.tap[dx], va, vb);
+            ws.cur[o] = (uint8_t)va;
+            ws.prev[o] = (uint8_t)vb;
         }
     } else {
         for (int o = lane; o < PATCH_PX; o += 32) {
             const int dy = o / PATCH, dx = o - dy * PATCH;
-            ws.cur[o] = (uint8_t)resize_px(c0, W, s, ws.tap[dy], ws.tap[dx]);
-            ws.prev[o] = (uint8_t)resize_px(p0, W, s, ws.tap[dy], ws.tap[dx]);
+            int va, vb;
+            resize_px_pair(c0, p0, W, s, ws.tap[dy], ws.tap[dx], va, vb);
+            ws.cur[o] = (uint8_t)va;
+            ws.prev[o] = (uint8_t)vb;
         }
     }
     __syncwarp();

@@ -227,8 +227,10 @@ int hh_extract_pair(const uint8_t* cur, const uint8_t* prev, int w, int h, int l
         const uint8_t* c0 = cur + (size_t)(yi - half) * w + (xi - half);
         const uint8_t* p0 = prev + (size_t)(yi - half) * w + (xi - half);
         for (int o = 0; o < PATCH * PATCH; o++) {
-            a19[o] = (uint8_t)resize_px(c0, w, side, tap[o / PATCH], tap[o % PATCH]);
-            b19[o] = (uint8_t)resize_px(p0, w, side, tap[o / PATCH], tap[o % PATCH]);
+            int va, vb;
+            resize_px_pair(c0, p0, w, side, tap[o / PATCH], tap[o % PATCH], va, vb);
+            a19[o] = (uint8_t)va; b19[o] = (uint8_t)vb;
+            if (va != resize_px(c0, w, side, tap[o / PATCH], tap[o % PATCH])) abort();
         }
         for (int i = 0; i < 64; i++) if (mip_ssd(a19, b19, i >> 3, i & 7) > 288) mot[i >> 3] |= (uint8_t)(1u << (i & 7));
         if (n < cap) {
