@@ -144,9 +144,10 @@ constexpr int PB_THREADS = 256;
 constexpr int PB_LIST = PEND_CAP;  // tie candidates of one (pair, layer) staged in shared memory per sweep
 
 __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
-    __shared__ uint32_t list[PB_LIST];
+    __shared__ uint32_t list[2][PB_LIST];       // undecided tie candidates of this round / of the next round
+    __shared__ uint32_t passed[PB_LIST];        // this round's winners, re-packed so that the scans run on full warps
     __shared__ uint8_t verdict[PB_LIST];
-    __shared__ int n_list, n_left, more;
+    __shared__ int n_list, n_next, n_pass, more;
     PairView pv; pv.g = &g; pv.m = m; pv.f = blockIdx.x;
     const uint32_t cap = (uint32_t)g.cand_cap;
     for (int li = 0; li < N_LAYERS; li++) {
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
             uint32_t next_cursor = end;
             if (listed) {
                 const uint32_t* src = cb.pend_list + (size_t)(pv.f * N_LAYERS + li) * PEND_CAP;
-                for (uint32_t i = threadIdx.x; i < n_pending; i += PB_THREADS) list[i] = src[i];
+                for (uint32_t i = threadIdx.x; i < n_pending; i += PB_THREADS) list[0][i] = src[i];
                 if (threadIdx.x == 0) n_list = (int)n_pending;
             } else
             // gather up to PB_LIST pending candidates starting at cursor, preserving order
@@ -183,15 +184,17 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
                 for (int w = 0; w < PB_THREADS / 32; w++) total += warp_cnt[w];
                 const int slot = before + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
                 const bool fits = n_list + total <= PB_LIST;
-                if (pend && fits) list[slot] = c;
+                if (pend && fits) list[0][slot] = c;
                 __syncthreads();
                 if (!fits) { next_cursor = base; if (threadIdx.x == 0) more = 1; break; }
                 if (threadIdx.x == 0) n_list += total;
                 __syncthreads();
             }
             __syncthreads();
-            // fixed point over this chunk; the list is re-packed after every round so that later rounds stay dense
-            int nl = n_list;
+            // fixed point over this chunk: every round decides all candidates whose raster-earlier tie neighbours are
+            // final (from the previous round's statuses), re-packs the winners and the still-waiting ones, then runs the
+            // scans of the winners one per thread
+            int nl = n_list, cur = 0;
 #ifdef MFK_PB_STATS
             int rounds = 0;
             if (threadIdx.x == 0) atomicAdd(&cb.counters[5], (uint32_t)nl);
@@ -201,8 +204,9 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
                 rounds++;
                 if (threadIdx.x == 0) { atomicAdd(&cb.counters[4], 1u); atomicAdd(&cb.counters[7], (uint32_t)nl); }
 #endif
+                if (threadIdx.x == 0) { n_next = 0; n_pass = 0; }
                 for (int i = threadIdx.x; i < nl; i += PB_THREADS) {
-                    const uint32_t c = list[i];
+                    const uint32_t c = list[cur][i];
                     const uint32_t xy = cb.xy[c];
                     const int x = xy & 0xffff, y = xy >> 16;
                     TieWindow tw;
@@ -210,27 +214,25 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
                     verdict[i] = earlier_pending_nearby(tw) ? 0 : (tie_break(tw) ? 2 : 1);
                 }
                 __syncthreads();
-                if (threadIdx.x == 0) n_left = 0;
-                __syncthreads();
-                // apply this round's verdicts (they were all taken from the previous round's statuses)
-                for (int i0 = 0; i0 < nl; i0 += PB_THREADS) {
-                    const int i = i0 + threadIdx.x;
-                    uint32_t c = 0;
-                    uint8_t v = 3;
-                    if (i < nl) { c = list[i]; v = verdict[i]; }
-                    if (v == 1 || v == 2) {
+                for (int i = threadIdx.x; i < nl; i += PB_THREADS) {
+                    const uint32_t c = list[cur][i];
+                    const uint8_t v = verdict[i];
+                    if (v == 0) list[cur ^ 1][atomicAdd(&n_next, 1)] = c;          // still waiting (order is irrelevant)
+                    else if (v == 2) passed[atomicAdd(&n_pass, 1)] = c;
+                    else {
                         const uint32_t xy = cb.xy[c];
-                        const int x = xy & 0xffff, y = xy >> 16;
-                        if (v == 2) after_max2d(pv, cb, tb, li, x, y, c);
-                        else { pv.m.status[pv.off(li) + y * L.w + x] = 0; cb.flags[c] = 0; }
+                        pv.m.status[pv.off(li) + (xy >> 16) * L.w + (xy & 0xffff)] = 0; cb.flags[c] = 0;
                     }
-                    __syncthreads();        // every thread has read its list entry before slots are reused
-                    if (v == 0) list[atomicAdd(&n_left, 1)] = c;        // still waiting: keep (order is irrelevant)
-                    __syncthreads();
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < n_pass; i += PB_THREADS) {
+                    const uint32_t c = passed[i];
+                    const uint32_t xy = cb.xy[c];
+                    after_max2d(pv, cb, tb, li, xy & 0xffff, xy >> 16, c);
                 }
                 __threadfence_block();
                 __syncthreads();
-                nl = n_left;
+                nl = n_next; cur ^= 1;
                 __syncthreads();
             }
 #ifdef MFK_PB_STATS
