@@ -69,4 +69,22 @@ __device__ __forceinline__ int oast_score_packed(const uint32_t r[16], const uin
     return min(254, max(0, s));
 }
 
+
+// Upper bound of the OAST-9/16 score from the 8 antipodal ring pairs: an arc of 9 contiguous ring pixels contains at
+// least one pixel of every pair (j, j+8), so  min_arc v - p <= min_j max(v_j, v_{j+8}) - p  (and the mirrored statement
+// for the darker test).  In the packed (v, 255 - v) form both bounds come out of 8 packed maxima and 4 packed 3-input
+// minima.  A bound <= 1 proves S = 0 without evaluating the 16 arcs.
+__device__ __forceinline__ int oast_score_bound_packed(const uint32_t r[16], const uint32_t centre) {
+    uint32_t m[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) m[j] = __vimax3_u16x2(r[j], r[j + 8], r[j]);
+    const uint32_t a = __vimin3_u16x2(m[0], m[1], m[2]), b = __vimin3_u16x2(m[3], m[4], m[5]);
+    const uint32_t c = __vimin3_u16x2(m[6], m[7], a);
+    const uint32_t lo = __vimin3_u16x2(b, c, c);
+    const int p = (int)(centre & 0xffffu);
+    const int brighter = (int)(lo & 0xffffu) - p;
+    const int darker = (int)(lo >> 16) - (255 - p);
+    return max(brighter, darker) - 1;
+}
+
 }  // namespace mfk

@@ -92,6 +92,7 @@ struct Harness {
                         for (int i = 0; i < 16; i++) { const uint32_t v = im[(y + RY[i]) * L.w + x + RX[i]]; r[i] = v | ((255u - v) << 16); }
                         const uint32_t v = im[y * L.w + x];
                         s = oast_score_packed(r, v | ((255u - v) << 16));
+                        if (oast_score_bound_packed(r, v | ((255u - v) << 16)) <= 0 && s != 0) abort();   // the bound must be sound
                     }
                     S[L.base + y * L.w + x] = (uint8_t)s;
                     if (s >= BRISK_THRESHOLD) { xy.push_back((uint32_t)x | ((uint32_t)y << 16)); meta.push_back((uint32_t)l); row_count[L.row0 + y]++; }
