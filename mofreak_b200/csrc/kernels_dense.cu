@@ -130,8 +130,14 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
         *reinterpret_cast<uint4*>(&tile[r][4 * k]) = q;
     }
     __syncthreads();
-    // ---- score: per-thread invariants are hoisted so that a pixel costs its 17 shared loads, the 40 packed
-    // min/max and a handful of other instructions (the kernel sits on the ALU pipe) ----
+    // ---- score, in two steps so that the 16-arc evaluation only runs where it can matter, on full warps:
+    //   1. every pixel: ring loads + antipodal-pair bound (12 packed ops).  bound <= 0 proves S = 0 (most pixels of a
+    //      difference image: flat or noise).  The others are queued in shared memory.
+    //   2. the queue: full closed-form score (40 packed ops), score store, hit count.
+    // Per-thread invariants are hoisted; the kernel sits on the ALU pipe.
+    __shared__ uint16_t hard[SC_TW * SC_TH];
+    __shared__ int n_hard;
+    if (tid == 0) n_hard = 0;
     const uint32_t* t0 = &tile[threadIdx.y + 3][threadIdx.x + 4];      // centre of this thread's first pixel
     const int xa = x0 + threadIdx.x, ya = y0 + threadIdx.y;
     uint8_t* Sp = S_all + L.base + (size_t)f * L.px + (size_t)ya * w + xa;
@@ -142,12 +148,11 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
         in_x[jx] = x >= 3 && x < w - 3;
         st_x[jx] = x < w;
     }
-    uint32_t* rc = row_count + (size_t)f * g.rows + L.row0 + ya;
+    __syncthreads();
 #pragma unroll
     for (int jy = 0; jy < SC_TH / 8; jy++) {
         const int y = ya + 8 * jy;
         const bool in_y = y >= 3 && y < h - 3, st_y = y < h;
-        unsigned row_hits = 0;
 #pragma unroll
         for (int jx = 0; jx < SC_TW / 32; jx++) {
             const uint32_t* c = t0 + (8 * jy) * SC_SW + 32 * jx;
@@ -157,14 +162,34 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
             r[4] = c[-3 * SC_SW];         r[5] = c[-3 * SC_SW + 1];     r[6] = c[-2 * SC_SW + 2];     r[7] = c[-SC_SW + 3];
             r[8] = c[3];                  r[9] = c[SC_SW + 3];          r[10] = c[2 * SC_SW + 2];     r[11] = c[3 * SC_SW + 1];
             r[12] = c[3 * SC_SW];         r[13] = c[3 * SC_SW - 1];     r[14] = c[2 * SC_SW - 2];     r[15] = c[SC_SW - 3];
-            int sc = oast_score_packed(r, c[0]);
             const bool inside = in_y && in_x[jx];
-            sc = inside ? sc : 0;
-            if (st_y && st_x[jx]) Sp[(8 * jy) * w + 32 * jx] = (uint8_t)sc;
-            // one warp = one tile row segment: count its hits with a ballot
-            row_hits += __popc(__ballot_sync(0xffffffffu, sc >= BRISK_THRESHOLD));
+            const bool is_hard = inside && oast_score_bound_packed(r, c[0]) > 0;
+            if (!is_hard && st_y && st_x[jx]) Sp[(8 * jy) * w + 32 * jx] = 0;
+            const unsigned mask = __ballot_sync(0xffffffffu, is_hard);
+            if (mask) {
+                int base = 0;
+                if (threadIdx.x == 0) base = atomicAdd(&n_hard, __popc(mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (is_hard) hard[base + __popc(mask & ((1u << threadIdx.x) - 1u))] =
+                    (uint16_t)(((threadIdx.y + 8 * jy) << 6) | (threadIdx.x + 32 * jx));
+            }
         }
-        if (threadIdx.x == 0 && row_hits) atomicAdd(rc + 8 * jy, row_hits);
+    }
+    __syncthreads();
+    const int nh = n_hard;
+    uint8_t* S = S_all + L.base + (size_t)f * L.px;
+    uint32_t* rc = row_count + (size_t)f * g.rows + L.row0;
+    for (int i = tid; i < nh; i += 256) {
+        const int ly = hard[i] >> 6, lx = hard[i] & 63;
+        const uint32_t* c = &tile[ly + 3][lx + 4];
+        uint32_t r[16];
+        r[0] = c[-3];                 r[1] = c[-SC_SW - 3];         r[2] = c[-2 * SC_SW - 2];     r[3] = c[-3 * SC_SW - 1];
+        r[4] = c[-3 * SC_SW];         r[5] = c[-3 * SC_SW + 1];     r[6] = c[-2 * SC_SW + 2];     r[7] = c[-SC_SW + 3];
+        r[8] = c[3];                  r[9] = c[SC_SW + 3];          r[10] = c[2 * SC_SW + 2];     r[11] = c[3 * SC_SW + 1];
+        r[12] = c[3 * SC_SW];         r[13] = c[3 * SC_SW - 1];     r[14] = c[2 * SC_SW - 2];     r[15] = c[SC_SW - 3];
+        const int sc = oast_score_packed(r, c[0]);
+        S[(y0 + ly) * w + x0 + lx] = (uint8_t)sc;
+        if (sc >= BRISK_THRESHOLD) atomicAdd(rc + y0 + ly, 1u);
     }
 }
 
