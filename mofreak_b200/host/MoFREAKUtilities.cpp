@@ -82,7 +82,7 @@ void formatMoFREAKRow(std::string& out, float x, float y, int frame, float scale
     out += '\n';
 }
 
-MoFREAKUtilities::MoFREAKUtilities(int dset) : current_action(0), dataset(dset), device_(0), ctx_(nullptr), ctx_w_(0), ctx_h_(0) {}
+MoFREAKUtilities::MoFREAKUtilities(int dset) : current_action(0), dataset(dset), device_(0), ctx_(nullptr), ctx_w_(0), ctx_h_(0), budget_scale_(1) {}
 
 MoFREAKUtilities::~MoFREAKUtilities() { mfk_destroy(ctx_); }
 
@@ -92,15 +92,21 @@ void MoFREAKUtilities::die(const std::string& what) {
     exit(1);
 }
 
-void MoFREAKUtilities::ensureContext(int width, int height) {
-    if (ctx_ && ctx_w_ == width && ctx_h_ == height) return;
+void MoFREAKUtilities::ensureContext(int width, int height, int budget_scale) {
+    if (budget_scale == 0) budget_scale = budget_scale_;
+    if (ctx_ && ctx_w_ == width && ctx_h_ == height && budget_scale == budget_scale_) return;
     mfk_destroy(ctx_);
     ctx_ = nullptr;
     // a store window of 69 frames = 64 pairs per launch sequence plus the 5-frame look-back
     const int pairs = 64;
-    if (mfk_create(&ctx_, device_, width, height, pairs + MFK_FRAME_GAP, pairs) != MFK_OK)
+    // default budgets of the C ABI (pyramid pixels / 6 candidates, / 48 rows per pair), scaled up after an overflow; every
+    // pyramid pixel being a candidate is the hard ceiling
+    const long pyr = (long)(width * (double)height * 1.9);
+    const int cand = budget_scale == 1 ? 0 : (int)std::min<long>(pyr, std::max<long>(4096, pyr / 6) * budget_scale);
+    const int rows = budget_scale == 1 ? 0 : (int)std::min<long>(pyr, std::max<long>(1024, pyr / 48) * budget_scale);
+    if (mfk_create_ex(&ctx_, device_, width, height, pairs + MFK_FRAME_GAP, pairs, cand, rows) != MFK_OK)
         die(std::string("mofreak_b200: ") + mfk_last_error(nullptr));
-    ctx_w_ = width; ctx_h_ = height;
+    ctx_w_ = width; ctx_h_ = height; budget_scale_ = budget_scale;
 }
 
 void MoFREAKUtilities::computeMoFREAKFromFile(std::string video_filename, std::string mofreak_filename, bool clear_features_after_computation) {
@@ -121,7 +127,11 @@ void MoFREAKUtilities::computeMoFREAKFromFrames(const uint8_t* gray, int width, 
     for (;;) {
         last_rows_.resize(cap);
         rc = mfk_extract_clip(ctx_, gray, (size_t)width, n_frames, last_rows_.data(), cap, &n);
-        if (rc == MFK_ERR_CAPACITY && n > cap) { cap = n; continue; }     // the caller's buffer was too small: retry once with the exact size
+        if (rc == MFK_ERR_CAPACITY && n > cap) { cap = n; continue; }     // the caller's buffer was too small: retry with the exact size
+        if (rc == MFK_ERR_CAPACITY && budget_scale_ < 64) {                 // a device-side budget overflowed (very busy frames):
+            ensureContext(width, height, budget_scale_ * 4);                // the reference has no such limit, so grow and redo
+            continue;
+        }
         break;
     }
     if (rc != MFK_OK) die(std::string("mofreak_b200: ") + mfk_last_error(ctx_));

@@ -76,7 +76,7 @@ public:
 
 private:
     void readMetadata(std::string filename, int& action, int& video_number, int& person);
-    void ensureContext(int width, int height);
+    void ensureContext(int width, int height, int budget_scale = 0);
     [[noreturn]] void die(const std::string& what);
 
     std::deque<MoFREAKFeature> features;
@@ -84,6 +84,7 @@ private:
     int device_;
     mfk_ctx* ctx_;
     int ctx_w_, ctx_h_;
+    int budget_scale_;     // 1, 4, 16, ... multiplier on the default per-pair candidate/row budgets
     std::vector<mfk_row> last_rows_;
 };
 

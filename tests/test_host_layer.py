@@ -157,3 +157,20 @@ def test_mip_facade_class(host, orc):
     host.mfkh_mip(clip[5].ctypes.data_as(C.c_void_p), clip[0].ctypes.data_as(C.c_void_p), 320, 240, C.c_float(17.3), 150, 100,
                   out.ctypes.data_as(C.c_void_p))
     assert np.array_equal(out, orc.mip_extract(clip[5], clip[0], 17.3, 150, 100))
+
+
+@pytest.mark.gpu
+def test_host_class_grows_device_budgets_for_busy_frames(host, orc, tmp_path):
+    """Quantised noise has far more detector candidates than the default per-pair budget; the reference has no such
+    limit, so the host class must grow the budgets and still write the reference's file."""
+    rng = np.random.default_rng(9)
+    w, h = 160, 120
+    frames = np.zeros((7, h, w), np.uint8)
+    frames[5] = (rng.integers(0, 4, (h, w)) * 80).astype(np.uint8)
+    frames[6] = (rng.integers(0, 3, (h, w)) * 100).astype(np.uint8)
+    video = tmp_path / "noise.y8"; out = tmp_path / "noise.mofreak"
+    host.mfkh_write_gray_video(str(video).encode(), frames.ctypes.data_as(C.c_void_p), w, h, 7)
+    n = host.mfkh_compute_mofreak_from_file(0, str(video).encode(), str(out).encode())
+    want = orc.extract_clip(frames)
+    assert n == len(want)
+    assert out.read_text() == orc.format_mofreak(want)
