@@ -129,6 +129,13 @@ int  mfk_bow_histogram(mfk_ctx* ctx, const uint8_t* desc, size_t N, uint32_t* co
  * MFK_ERR_STATE when the library was built without NCCL.  No counterpart in the reference. */
 int  mfk_allreduce_counts(mfk_ctx* ctx, uint32_t* d_counts, size_t n, void* nccl_comm);
 
+/* Helpers to build the communicator for mfk_allreduce_counts without linking NCCL (same run-time resolution): rank 0 calls
+ * mfk_nccl_unique_id and ships the 128 bytes to the other ranks by any means (torch.distributed, MPI, a file); every rank
+ * then calls mfk_nccl_comm_init with its context's device current. */
+int  mfk_nccl_unique_id(uint8_t id_out[128]);
+int  mfk_nccl_comm_init(mfk_ctx* ctx, void** nccl_comm_out, int n_ranks, int rank, const uint8_t id[128]);
+int  mfk_nccl_comm_destroy(void* nccl_comm);
+
 /* ---- measurement ------------------------------------------------------------------------------------ */
 
 /* CUDA-event stopwatch on the context's stream (torch.cuda.Event only sees torch's own streams). */

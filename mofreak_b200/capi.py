@@ -24,7 +24,7 @@ SYMBOLS = [
     "mfk_create", "mfk_create_ex", "mfk_destroy", "mfk_last_error", "mfk_sync", "mfk_upload_frames", "mfk_frame_store",
     "mfk_extract_pairs", "mfk_fetch_rows", "mfk_rows_device", "mfk_reset_rows", "mfk_extract_clip", "mfk_mip_describe",
     "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram",
-    "mfk_allreduce_counts", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read",
+    "mfk_allreduce_counts", "mfk_nccl_unique_id", "mfk_nccl_comm_init", "mfk_nccl_comm_destroy", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read",
     "mfk_set_serial", "mfk_launch_count", "mfk_debug_layer", "mfk_debug_keypoints", "mfk_debug_counters", "mfk_synth_clip", "mfk_freak_scale_index", "mfk_version",
 ]
 
@@ -71,6 +71,9 @@ def lib():
     L.mfk_bow_histogram_rows.argtypes = [p, u32p]
     L.mfk_bow_histogram.argtypes = [p, u8p, C.c_size_t, u32p]
     L.mfk_allreduce_counts.argtypes = [p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.mfk_nccl_unique_id.argtypes = [C.c_void_p]
+    L.mfk_nccl_comm_init.argtypes = [p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
+    L.mfk_nccl_comm_destroy.argtypes = [C.c_void_p]
     L.mfk_timer_start.argtypes = [p]
     L.mfk_timer_stop.argtypes = [p, C.POINTER(C.c_float)]
     L.mfk_profile_enable.argtypes = [p, C.c_int]
@@ -218,6 +221,24 @@ class Context:
         counts = np.zeros(self.K, np.uint32)
         self._check(self._L.mfk_bow_histogram_rows(self._h, _ptr(counts)))
         return counts
+
+    # --- multi-GPU exchange of word counts ---
+    @staticmethod
+    def nccl_unique_id():
+        buf = np.zeros(128, np.uint8)
+        rc = lib().mfk_nccl_unique_id(_ptr(buf))
+        if rc != MFK_OK:
+            raise MofreakError(rc, (lib().mfk_last_error(None) or b"").decode())
+        return buf
+
+    def nccl_comm_init(self, n_ranks, rank, unique_id):
+        comm = C.c_void_p()
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        self._check(self._L.mfk_nccl_comm_init(self._h, C.byref(comm), n_ranks, rank, _ptr(uid)))
+        return comm
+
+    def allreduce_counts(self, d_counts_ptr, n, comm):
+        self._check(self._L.mfk_allreduce_counts(self._h, C.c_void_p(d_counts_ptr), n, comm))
 
     # --- measurement ---
     def sync(self):

@@ -685,21 +685,58 @@ int mfk_bow_histogram_rows(mfk_ctx* c, uint32_t* counts) {
 
 // NCCL is resolved at run time so that the library loads on machines without it and shares the copy a host
 // process (e.g. torch) has already loaded.
+namespace {
+struct NcclId { char internal[128]; };
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_getid_fn)(NcclId*);
+typedef int (*nccl_init_fn)(void**, int, NcclId, int);
+typedef int (*nccl_destroy_fn)(void*);
+void* nccl_symbol(const char* name) {
+    static void* h = nullptr;
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    return h ? dlsym(h, name) : nullptr;
+}
+}  // namespace
+
 int mfk_allreduce_counts(mfk_ctx* c, uint32_t* d_counts, size_t n, void* nccl_comm) {
     if (!c || !d_counts || !nccl_comm) return fail(c, MFK_ERR_ARG, "bad argument to mfk_allreduce_counts");
-    typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-    static allreduce_fn fn = nullptr;
-    if (!fn) {
-        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        if (h) fn = (allreduce_fn)dlsym(h, "ncclAllReduce");
-        if (!fn) return fail(c, MFK_ERR_STATE, "NCCL is not available (libnccl.so.2 not found)");
-    }
+    static nccl_allreduce_fn fn = (nccl_allreduce_fn)nccl_symbol("ncclAllReduce");
+    if (!fn) return fail(c, MFK_ERR_STATE, "NCCL is not available (libnccl.so.2 not found)");
     CU(c, cudaSetDevice(c->device));
+    { const int rc = join_lanes(c); if (rc != MFK_OK) return rc; }
     const int ncclUint32 = 3, ncclSum = 0;      // nccl.h: ncclDataType_t / ncclRedOp_t
     const int r = fn(d_counts, d_counts, n, ncclUint32, ncclSum, nccl_comm, c->stream);
     if (r != 0) return fail(c, MFK_ERR_CUDA, "ncclAllReduce failed with code %d", r);
     return MFK_OK;
+}
+
+int mfk_nccl_unique_id(uint8_t id_out[128]) {
+    static nccl_getid_fn fn = (nccl_getid_fn)nccl_symbol("ncclGetUniqueId");
+    if (!fn || !id_out) return fail(nullptr, MFK_ERR_STATE, "NCCL is not available (libnccl.so.2 not found)");
+    NcclId id;
+    const int r = fn(&id);
+    if (r != 0) return fail(nullptr, MFK_ERR_CUDA, "ncclGetUniqueId failed with code %d", r);
+    memcpy(id_out, id.internal, 128);
+    return MFK_OK;
+}
+
+int mfk_nccl_comm_init(mfk_ctx* c, void** nccl_comm_out, int n_ranks, int rank, const uint8_t id_bytes[128]) {
+    if (!c || !nccl_comm_out || !id_bytes) return fail(c, MFK_ERR_ARG, "bad argument to mfk_nccl_comm_init");
+    static nccl_init_fn fn = (nccl_init_fn)nccl_symbol("ncclCommInitRank");
+    if (!fn) return fail(c, MFK_ERR_STATE, "NCCL is not available (libnccl.so.2 not found)");
+    CU(c, cudaSetDevice(c->device));
+    NcclId id;
+    memcpy(id.internal, id_bytes, 128);
+    const int r = fn(nccl_comm_out, n_ranks, id, rank);
+    if (r != 0) return fail(c, MFK_ERR_CUDA, "ncclCommInitRank failed with code %d", r);
+    return MFK_OK;
+}
+
+int mfk_nccl_comm_destroy(void* nccl_comm) {
+    static nccl_destroy_fn fn = (nccl_destroy_fn)nccl_symbol("ncclCommDestroy");
+    if (!fn || !nccl_comm) return MFK_ERR_ARG;
+    return fn(nccl_comm) == 0 ? MFK_OK : MFK_ERR_CUDA;
 }
 
 // ---- measurement ----------------------------------------------------------------------------------------
