@@ -80,7 +80,7 @@ struct mfk_ctx {
     int32_t *d_cur = nullptr, *d_prev = nullptr, *d_label = nullptr;
     size_t pair_cap = 0, pairs_queued = 0;
     DeviceTables tb{};
-    void* tb_alloc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* tb_alloc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint8_t* codebook = nullptr;
     int K = 0;
     uint32_t* bow_counts = nullptr;
@@ -180,6 +180,10 @@ int upload_tables(mfk_ctx* c) {
     CU(c, cudaMemcpy(thr, T.scale_threshold, sizeof T.scale_threshold, cudaMemcpyHostToDevice));
     CU(c, cudaMemcpy(op, T.orient, sizeof T.orient, cudaMemcpyHostToDevice));
     CU(c, cudaMemcpy(up, T.used, sizeof T.used, cudaMemcpyHostToDevice));
+    uint16_t* mn;
+    CU(c, dalloc(&mn, 2 * 361)); c->tb_alloc[5] = mn;
+    CU(c, cudaMemcpy(mn, T.mip_needed, sizeof T.mip_needed, cudaMemcpyHostToDevice));
+    c->tb.mip_needed = mn; c->tb.n_mip_needed = T.n_mip_needed;
     c->tb.points = pts; c->tb.pattern_size = ps; c->tb.scale_threshold = thr; c->tb.orient = op; c->tb.used = up;
     return MFK_OK;
 }
@@ -600,7 +604,7 @@ int mfk_mip_describe(mfk_ctx* c, int cur_slot, int prev_slot, const float* kp_xy
     const size_t px = (size_t)c->W * c->H;
     { Span s(c, P_MIP, 1);
       launch_mip_only(c->stream, c->W, c->H, c->store + (size_t)(cur_slot % c->store_frames) * px,
-                      c->store + (size_t)(prev_slot % c->store_frames) * px, d_kp, n, d_mot, d_err); }
+                      c->store + (size_t)(prev_slot % c->store_frames) * px, d_kp, n, d_mot, d_err, c->tb); }
     uint32_t herr = 0;
     CU(c, cudaMemcpyAsync(motion, d_mot, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, c->stream));

@@ -51,6 +51,8 @@ struct DeviceTables {             // device copies of mfk::Tables
     const float* scale_threshold;     // [64]
     const OrientPair* orient;         // [45]
     const UsedPair* used;             // [64]
+    const uint16_t* mip_needed;       // patch pixels the MIP tests read (tables.h)
+    int n_mip_needed;
 };
 
 // --- dense stage ------------------------------------------------------------------------------------
@@ -73,7 +75,7 @@ void launch_advance(cudaStream_t, const Geom&, CandBuf);              // counter
 void launch_describe(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, const uint8_t* img,
                      const int32_t* integral, CandBuf, DeviceTables, void* rows /*mfk_row*/);
 void launch_mip_only(cudaStream_t, int W, int H, const uint8_t* cur, const uint8_t* prev, const float* kp_xys, int n,
-                     uint8_t* motion, uint32_t* err_flag);
+                     uint8_t* motion, uint32_t* err_flag, DeviceTables);
 // --- bag of words --------------------------------------------------------------------------------------
 void launch_bow_assign(cudaStream_t, const uint8_t* desc, size_t stride_bytes, size_t n, const uint8_t* codebook, int K,
                        int32_t* idx, uint32_t* counts /*nullable*/);

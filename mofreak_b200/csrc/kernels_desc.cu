@@ -17,7 +17,7 @@ namespace {
 struct RowOut { float x, y; int32_t frame; float scale; uint32_t app[2]; uint32_t mot[2]; };   // == mfk_row
 
 constexpr int DW = 8;                 // warps per block
-constexpr int PATCH_PX = PATCH * PATCH, PATCH_PAD = 368;
+constexpr int PATCH_PAD = 368;        // 19 x 19 = 361 patch bytes, padded
 
 constexpr int ROI_MAX = 32;           // regions of interest up to this side are staged in shared memory
 
@@ -31,12 +31,13 @@ struct WarpScratch {
 // cv::resize(ROI s x s -> 19 x 19, INTER_LINEAR) for both frames into scratch (fixed-point bilinear of OpenCV's
 // imgwarp.cpp: 11-bit coefficients, vertical pass ((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2 >> 2)
 __device__ __forceinline__ void resize_roi_pair(WarpScratch& ws, const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
-                                                int W, int tl_x, int tl_y, int s, int lane) {
+                                                int W, int tl_x, int tl_y, int s, int lane, const DeviceTables& tb) {
     if (lane < PATCH) ws.tap[lane] = resize_tap(s, lane);
     __syncwarp();
     const uint8_t* c0 = cur + (size_t)tl_y * W + tl_x;
     const uint8_t* p0 = prev + (size_t)tl_y * W + tl_x;
-    if (s <= ROI_MAX) {
+    const bool staged = s <= ROI_MAX;
+    if (staged) {
         // stage both regions with 32-bit reads (8 lanes per row, 4 rows per step), then interpolate from shared memory
         for (int i = lane; i < s * 8; i += 32) {
             const int r = i >> 3, c4 = (i & 7) * 4;
@@ -46,21 +47,15 @@ __device__ __forceinline__ void resize_roi_pair(WarpScratch& ws, const uint8_t* 
             }
         }
         __syncwarp();
-        for (int o = lane; o < PATCH_PX; o += 32) {
-            const int dy = o / PATCH, dx = o - dy * PATCH;
-            int va, vb;
-            resize_px_pair(ws.roi[0], ws.roi[1], ROI_MAX, s, ws.tap[dy], ws.tap[dx], va, vb);
-            ws.cur[o] = (uint8_t)va;
-            ws.prev[o] = (uint8_t)vb;
-        }
-    } else {
-        for (int o = lane; o < PATCH_PX; o += 32) {
-            const int dy = o / PATCH, dx = o - dy * PATCH;
-            int va, vb;
-            resize_px_pair(c0, p0, W, s, ws.tap[dy], ws.tap[dx], va, vb);
-            ws.cur[o] = (uint8_t)va;
-            ws.prev[o] = (uint8_t)vb;
-        }
+    }
+    // only the 276 of the 2 x 361 patch pixels that the SSD tests read are interpolated
+    for (int i = lane; i < tb.n_mip_needed; i += 32) {
+        const int e = tb.mip_needed[i];
+        const int fr = e >> 15, p = e & 0x7fff;
+        const int dy = p / PATCH, dx = p - dy * PATCH;
+        const int v = staged ? resize_px(ws.roi[fr], ROI_MAX, s, ws.tap[dy], ws.tap[dx])
+                             : resize_px(fr ? p0 : c0, W, s, ws.tap[dy], ws.tap[dx]);
+        (fr ? ws.prev : ws.cur)[p] = (uint8_t)v;
     }
     __syncwarp();
 }
@@ -129,7 +124,7 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
         const int xi = (int)kx, yi = (int)ky;                          // float -> int at the call, :460
         const int half = (int)ksize / 2;
         const int side = (int)ceilf(ksize);
-        resize_roi_pair(ws, cur, prev, g.W, xi - half, yi - half, side, lane);
+        resize_roi_pair(ws, cur, prev, g.W, xi - half, yi - half, side, lane, tb);
         uint32_t mot[2];
         mip_bits(ws, lane, mot);
 
@@ -153,7 +148,7 @@ void launch_describe(cudaStream_t st, const Geom& g, const uint8_t* store, int s
 // MIP bytes for caller-supplied keypoints on one frame pair (the MotionInterchangePatterns facade).
 __global__ void __launch_bounds__(DW * 32)
 k_mip_only(int W, int H, const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev, const float* __restrict__ kp, int n,
-           uint8_t* __restrict__ motion, uint32_t* __restrict__ err) {
+           uint8_t* __restrict__ motion, uint32_t* __restrict__ err, DeviceTables tb) {
     __shared__ WarpScratch scratch[DW];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpScratch& ws = scratch[wib];
@@ -166,7 +161,7 @@ k_mip_only(int W, int H, const uint8_t* __restrict__ cur, const uint8_t* __restr
             if (lane == 0) { atomicOr(err, 1u); for (int i = 0; i < 8; i++) motion[8 * r + i] = 0; }
             continue;
         }
-        resize_roi_pair(ws, cur, prev, W, tl_x, tl_y, side, lane);
+        resize_roi_pair(ws, cur, prev, W, tl_x, tl_y, side, lane, tb);
         uint32_t mot[2];
         mip_bits(ws, lane, mot);
         if (lane == 0) {
@@ -177,10 +172,10 @@ k_mip_only(int W, int H, const uint8_t* __restrict__ cur, const uint8_t* __restr
 }
 
 void launch_mip_only(cudaStream_t st, int W, int H, const uint8_t* cur, const uint8_t* prev, const float* kp_xys, int n,
-                     uint8_t* motion, uint32_t* err_flag) {
+                     uint8_t* motion, uint32_t* err_flag, DeviceTables tb) {
     if (n <= 0) return;
     const int blocks = min((n + DW - 1) / DW, 148 * 4);
-    k_mip_only<<<blocks, DW * 32, 0, st>>>(W, H, cur, prev, kp_xys, n, motion, err_flag);
+    k_mip_only<<<blocks, DW * 32, 0, st>>>(W, H, cur, prev, kp_xys, n, motion, err_flag, tb);
 }
 
 }  // namespace mfk

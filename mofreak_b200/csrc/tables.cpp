@@ -112,6 +112,27 @@ void fill_used_pairs(Tables& T) {
         }
 }
 
+void fill_mip_needed(Tables& T) {
+    // centres MoFREAKUtilities.cpp:307-316, shifts :55-70; each test reads 9 consecutive bytes from the top-left corner of
+    // its 3x3 region of the row-major 19x19 buffer (:79-88)
+    static const int CX[8] = {5, 5, 5, 9, 9, 13, 13, 13}, CY[8] = {5, 9, 13, 5, 13, 5, 9, 13};
+    static const int SX[8] = {-4, -3, 0, 3, 4, 3, 0, -3}, SY[8] = {0, 3, 4, 3, 0, -3, -4, -3};
+    bool need[2][361] = {};
+    for (int c = 0; c < 8; c++) {
+        const int s = (CY[c] - 1) * 19 + CX[c] - 1;
+        for (int i = 0; i < 9; i++) need[0][s + i] = true;
+        for (int k = 0; k < 8; k++) {
+            const int q = (CY[c] + SY[k] - 1) * 19 + CX[c] + SX[k] - 1;
+            for (int i = 0; i < 9; i++) need[1][q + i] = true;
+        }
+    }
+    int n = 0;
+    for (int fr = 0; fr < 2; fr++)
+        for (int p = 0; p < 361; p++)
+            if (need[fr][p]) T.mip_needed[n++] = (uint16_t)(p | (fr << 15));
+    T.n_mip_needed = n;
+}
+
 inline float bits_to_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline uint32_t float_to_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
@@ -161,6 +182,7 @@ const Tables& tables() {
         fill_points(*T);
         fill_orientation_pairs(*T);
         fill_used_pairs(*T);
+        fill_mip_needed(*T);
         g_tables = T;                 // scale_index_from_table() is not used while filling
         fill_scale_thresholds(*T);
     });

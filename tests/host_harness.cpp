@@ -64,7 +64,7 @@ struct Harness {
         maps.img = img.data(); maps.S = S.data(); maps.seen = seen.data(); maps.status = status.data();
         const Tables& T = tables();
         tb.points = T.points; tb.pattern_size = T.pattern_size; tb.scale_threshold = T.scale_threshold;
-        tb.orient = T.orient; tb.used = T.used;
+        tb.orient = T.orient; tb.used = T.used; tb.mip_needed = T.mip_needed; tb.n_mip_needed = T.n_mip_needed;
     }
 
     void dense(const uint8_t* diff) {
@@ -227,11 +227,11 @@ int hh_extract_pair(const uint8_t* cur, const uint8_t* prev, int w, int h, int l
         for (int d = 0; d < PATCH; d++) tap[d] = resize_tap(side, d);
         const uint8_t* c0 = cur + (size_t)(yi - half) * w + (xi - half);
         const uint8_t* p0 = prev + (size_t)(yi - half) * w + (xi - half);
-        for (int o = 0; o < PATCH * PATCH; o++) {
-            int va, vb;
-            resize_px_pair(c0, p0, w, side, tap[o / PATCH], tap[o % PATCH], va, vb);
-            a19[o] = (uint8_t)va; b19[o] = (uint8_t)vb;
-            if (va != resize_px(c0, w, side, tap[o / PATCH], tap[o % PATCH])) abort();
+        memset(a19, 0xEE, sizeof a19); memset(b19, 0xEE, sizeof b19);      // pixels the SSD tests never read stay unset
+        for (int i = 0; i < H.tb.n_mip_needed; i++) {
+            const int e = H.tb.mip_needed[i], fr = e >> 15, p = e & 0x7fff;
+            const int v = resize_px(fr ? p0 : c0, w, side, tap[p / PATCH], tap[p % PATCH]);
+            (fr ? b19 : a19)[p] = (uint8_t)v;
         }
         for (int i = 0; i < 64; i++) if (mip_ssd(a19, b19, i >> 3, i & 7) > 288) mot[i >> 3] |= (uint8_t)(1u << (i & 7));
         if (n < cap) {
