@@ -53,16 +53,59 @@ void launch_absdiff(cudaStream_t st, const Geom& g, const uint8_t* store, int st
 // ---------------------------------------------------------------------------------------------------
 // pyramid samplers, one destination pixel per thread
 // ---------------------------------------------------------------------------------------------------
-template <bool TWOTHIRD>
-__global__ void k_downsample(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base, int sw, int spx,
-                             int dw, int dh, int dpx) {
+// half sampling, 4 destination pixels per thread: inside the paired 16-byte blocks the rule is the same for every
+// column (avg of avg, all rounding up), so two unaligned 8-byte reads give four outputs; the few columns of the odd
+// trailing block and of the leftover use the per-pixel function.
+__global__ void k_half(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base, int sw, int spx, int dw, int dh, int dpx) {
     const int f = blockIdx.z;
-    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int oy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (ox >= dw || oy >= dh) return;
+    if (ox0 >= dw || oy >= dh) return;
     const uint8_t* src = src_base + (size_t)f * spx;
-    const int v = TWOTHIRD ? twothird_px(src, sw, ox, oy) : half_px(src, sw, ox, oy);
-    dst_base[(size_t)f * dpx + oy * dw + ox] = (uint8_t)v;
+    uint8_t* dst = dst_base + (size_t)f * dpx + oy * dw + ox0;
+    const int paired_out = ((sw >> 4) >> 1) * 16;
+    if (ox0 + 3 < paired_out) {
+        uint32_t u0, u1, l0, l1;
+        load8(src + (2 * oy) * sw + 2 * ox0, u0, u1);
+        load8(src + (2 * oy + 1) * sw + 2 * ox0, l0, l1);
+        const uint32_t v0 = __vavgu4(u0, l0), v1 = __vavgu4(u1, l1);      // vertical averages of 8 columns, rounding up
+        // horizontal: avg(v[2j], v[2j+1]) — pair the even and the odd bytes
+        const uint32_t ev = __byte_perm(v0, v1, 0x6420), od = __byte_perm(v0, v1, 0x7531);
+        const uint32_t r = __vavgu4(ev, od);
+        dst[0] = (uint8_t)r; dst[1] = (uint8_t)(r >> 8); dst[2] = (uint8_t)(r >> 16); dst[3] = (uint8_t)(r >> 24);
+    } else {
+        for (int k = 0; k < 4 && ox0 + k < dw; k++) dst[k] = (uint8_t)half_px(src, sw, ox0 + k, oy);
+    }
+}
+
+// two-third sampling, one 3x3 source block -> 2x2 destination block per thread (9 loads for 4 outputs)
+__global__ void k_twothird(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base, int sw, int spx, int dw, int dh, int dpx) {
+    const int f = blockIdx.z;
+    const int tc = blockIdx.x * blockDim.x + threadIdx.x;       // column triple
+    const int tr = blockIdx.y * blockDim.y + threadIdx.y;       // row triple
+    if (2 * tc >= dw || 2 * tr >= dh) return;
+    const uint8_t* r1 = src_base + (size_t)f * spx + (3 * tr) * sw + 3 * tc;
+    const uint8_t* r2 = r1 + sw;
+    const uint8_t* r3 = r2 + sw;
+    uint8_t* d1 = dst_base + (size_t)f * dpx + (2 * tr) * dw + 2 * tc;
+    uint8_t* d2 = d1 + dw;
+    const int a0 = r1[0], a1 = r1[1], a2 = r1[2], b0 = r2[0], b1 = r2[1], b2 = r2[2], c0 = r3[0], c1 = r3[1], c2 = r3[2];
+    const int blocks = sw / 15;
+    if (tc < 5 * blocks) {
+        // inside a 15-column block: avg(avg(a,b),a) chains, vertically then horizontally; the fifth triple takes its
+        // middle sample from the block's byte 12, i.e. from its own first column (brisk.cpp:1982-1983)
+        const bool fifth = (tc % 5) == 4;
+        const int u0 = avg_up(avg_up(a0, b0), a0), u2 = avg_up(avg_up(a2, b2), a2);
+        const int l0 = avg_up(avg_up(c0, b0), c0), l2 = avg_up(avg_up(c2, b2), c2);
+        const int um = fifth ? u0 : avg_up(avg_up(a1, b1), a1);
+        const int lm = fifth ? l0 : avg_up(avg_up(c1, b1), c1);
+        d1[0] = (uint8_t)avg_up(avg_up(u0, um), u0); d1[1] = (uint8_t)avg_up(avg_up(u2, um), u2);
+        d2[0] = (uint8_t)avg_up(avg_up(l0, lm), l0); d2[1] = (uint8_t)avg_up(avg_up(l2, lm), l2);
+    } else {
+        // trailing triples: (4A + 2(B+C) + D) / 9 (brisk.cpp:2036-2051)
+        d1[0] = (uint8_t)((4 * a0 + 2 * (a1 + b0) + b1) / 9); d1[1] = (uint8_t)((4 * a2 + 2 * (a1 + b2) + b1) / 9);
+        d2[0] = (uint8_t)((4 * c0 + 2 * (c1 + b0) + b1) / 9); d2[1] = (uint8_t)((4 * c2 + 2 * (c1 + b2) + b1) / 9);
+    }
 }
 
 void launch_pyramid(cudaStream_t st, const Geom& g, uint8_t* img) {
@@ -72,11 +115,13 @@ void launch_pyramid(cudaStream_t st, const Geom& g, uint8_t* img) {
         const LayerGeom& D = g.L[l];
         const LayerGeom& S = g.L[SRC[l]];
         dim3 block(32, 8);
-        dim3 grid((D.w + 31) / 32, (D.h + 7) / 8, g.F);
-        if (l == 1)
-            k_downsample<true><<<grid, block, 0, st>>>(img + S.base, img + D.base, S.w, S.px, D.w, D.h, D.px);
-        else
-            k_downsample<false><<<grid, block, 0, st>>>(img + S.base, img + D.base, S.w, S.px, D.w, D.h, D.px);
+        if (l == 1) {
+            dim3 grid((D.w / 2 + 31) / 32, (D.h / 2 + 7) / 8, g.F);
+            k_twothird<<<grid, block, 0, st>>>(img + S.base, img + D.base, S.w, S.px, D.w, D.h, D.px);
+        } else {
+            dim3 grid(((D.w + 3) / 4 + 31) / 32, (D.h + 7) / 8, g.F);
+            k_half<<<grid, block, 0, st>>>(img + S.base, img + D.base, S.w, S.px, D.w, D.h, D.px);
+        }
     }
 }
 
