@@ -59,7 +59,8 @@ struct mfk_ctx {
     struct Lane {
         Maps maps{};
         int32_t* integral = nullptr;
-        int32_t* integral_left = nullptr;     // per image row: sums left of each 32-column strip
+        int32_t* integral_left = nullptr;
+        unsigned long long* hitmask = nullptr;  // detector hits, one 64-bit word per (pair, layer row, 64-column tile)     // per image row: sums left of each 32-column strip
         CandBuf cb{};
         uint32_t* scan_scratch = nullptr;
         cudaStream_t stream = nullptr, aux_stream = nullptr;
@@ -235,7 +236,6 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
     mfk_ctx::Lane& L = c->lane[li];
     mfk_ctx::Lane& P = c->lane[c->last_lane];            // lane of the previous batch
     cudaStream_t st = L.stream;
-    CU(c, cudaMemsetAsync(L.cb.row_count, 0, ((size_t)F * g.rows + 1) * sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(L.maps.seen, 0, (size_t)F * g.pyr_px, st));
     CU(c, cudaMemsetAsync(L.cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(L.cb.q_count, 0, 4 * sizeof(uint32_t), st));
@@ -250,9 +250,10 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
         CU(c, cudaEventRecord(L.aux_join, L.aux_stream));
     }
     { Span s(c, P_PYRAMID, 5, st);   launch_pyramid(st, g, L.maps.img); }
-    { Span s(c, P_SCORES, 1, st);    launch_scores(st, g, L.maps.img, L.maps.S, L.cb.row_count); }
-    { Span s(c, P_SCAN, 3, st);      launch_exclusive_scan(st, L.cb.row_count, F * g.rows, nullptr, L.scan_scratch); }
-    { Span s(c, P_FILL, 1, st);      launch_fill_candidates(st, g, L.maps.S, L.cb); }
+    { Span s(c, P_SCORES, 1, st);    launch_scores(st, g, L.maps.img, L.maps.S, L.hitmask); }
+    { Span s(c, P_SCAN, 4, st);      launch_row_counts(st, g, L.hitmask, L.cb.row_count);
+                                     launch_exclusive_scan(st, L.cb.row_count, F * g.rows, nullptr, L.scan_scratch); }
+    { Span s(c, P_FILL, 1, st);      launch_fill_candidates(st, g, L.hitmask, L.cb); }
     { Span s(c, P_PHASE_A, 4, st);   launch_phase_a(st, g, L.maps, L.cb, c->tb); }
     { Span s(c, P_PHASE_B, 1, st);   launch_phase_b(st, g, L.maps, L.cb, c->tb); }
     // from here on the shared row accumulation is touched: wait until the previous batch has advanced it
@@ -283,7 +284,7 @@ void destroy(mfk_ctx* c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->store);
     for (auto& L : c->lane) {
-        cudaFree(L.maps.img); cudaFree(L.maps.S); cudaFree(L.maps.seen); cudaFree(L.maps.status); cudaFree(L.integral); cudaFree(L.integral_left);
+        cudaFree(L.maps.img); cudaFree(L.maps.S); cudaFree(L.maps.seen); cudaFree(L.maps.status); cudaFree(L.integral); cudaFree(L.integral_left); cudaFree(L.hitmask);
         cudaFree(L.cb.row_count); cudaFree(L.cb.xy); cudaFree(L.cb.meta); cudaFree(L.cb.kx); cudaFree(L.cb.ky); cudaFree(L.cb.ksize);
         cudaFree(L.cb.kresp); cudaFree(L.cb.flags); cudaFree(L.cb.scale_idx); cudaFree(L.cb.keep_scan); cudaFree(L.cb.row_src);
         cudaFree(L.cb.pend_count); cudaFree(L.cb.pend_list); cudaFree(L.cb.live);
@@ -394,6 +395,7 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
         CUC(dalloc(&L.maps.status, F * c->pyr_px + slack));
         CUC(dalloc(&L.integral, F * (size_t)(width + 1) * (height + 1)));
         CUC(dalloc(&L.integral_left, F * (size_t)height * ((width + 31) / 32)));
+        CUC(dalloc(&L.hitmask, F * (size_t)c->rows * score_mask_words(width)));
         CUC(dalloc(&L.cb.row_count, F * c->rows + 2));
         CUC(dalloc(&L.cb.xy, cand_cap)); CUC(dalloc(&L.cb.meta, cand_cap));
         CUC(dalloc(&L.cb.kx, cand_cap)); CUC(dalloc(&L.cb.ky, cand_cap));

@@ -58,8 +58,10 @@ struct DeviceTables {             // device copies of mfk::Tables
 // --- dense stage ------------------------------------------------------------------------------------
 void launch_absdiff(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, uint8_t* img);
 void launch_pyramid(cudaStream_t, const Geom&, uint8_t* img);                                  // layers 1..5
-void launch_scores(cudaStream_t, const Geom&, const uint8_t* img, uint8_t* S, uint32_t* row_count);
-void launch_fill_candidates(cudaStream_t, const Geom&, const uint8_t* S, CandBuf);
+int  score_mask_words(int frame_width);        // 64-bit hit-mask words per (pair, layer row)
+void launch_scores(cudaStream_t, const Geom&, const uint8_t* img, uint8_t* S, unsigned long long* hitmask);
+void launch_row_counts(cudaStream_t, const Geom&, const unsigned long long* hitmask, uint32_t* row_count);
+void launch_fill_candidates(cudaStream_t, const Geom&, const unsigned long long* hitmask, CandBuf);
 void launch_integral(cudaStream_t, const Geom&, const uint8_t* img /*layer 0*/, int32_t* integral,
                      int32_t* left /*F*H*ceil(W/32) scratch*/);
 // --- scans --------------------------------------------------------------------------------------------

@@ -147,7 +147,7 @@ struct ScoreTiles { int first[N_LAYERS + 1]; int across[N_LAYERS]; };   // tile 
 
 __global__ void __launch_bounds__(256)
 k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tiles, const uint8_t* __restrict__ img_all,
-         uint8_t* __restrict__ S_all, uint32_t* __restrict__ row_count) {
+         uint8_t* __restrict__ S_all, unsigned long long* __restrict__ hitmask, int mask_words) {
     __shared__ __align__(16) uint32_t tile[SC_SH][SC_SW];
     const int f = blockIdx.y;
     int l = 0;
@@ -181,8 +181,10 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     //   2. the queue: full closed-form score (40 packed ops), score store, hit count.
     // Per-thread invariants are hoisted; the kernel sits on the ALU pipe.
     __shared__ uint16_t hard[SC_TW * SC_TH];
+    __shared__ unsigned long long row_hits[SC_TH];      // bit x of word y: pixel (x0 + x, y0 + y) is a detector hit
     __shared__ int n_hard;
     if (tid == 0) n_hard = 0;
+    if (tid < SC_TH) row_hits[tid] = 0ull;
     const uint32_t* t0 = &tile[threadIdx.y + 3][threadIdx.x + 4];      // centre of this thread's first pixel
     const int xa = x0 + threadIdx.x, ya = y0 + threadIdx.y;
     uint8_t* Sp = S_all + L.base + (size_t)f * L.px + (size_t)ya * w + xa;
@@ -223,7 +225,6 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     __syncthreads();
     const int nh = n_hard;
     uint8_t* S = S_all + L.base + (size_t)f * L.px;
-    uint32_t* rc = row_count + (size_t)f * g.rows + L.row0;
     for (int i = tid; i < nh; i += 256) {
         const int ly = hard[i] >> 6, lx = hard[i] & 63;
         const uint32_t* c = &tile[ly + 3][lx + 4];
@@ -234,11 +235,17 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
         r[12] = c[3 * SC_SW];         r[13] = c[3 * SC_SW - 1];     r[14] = c[2 * SC_SW - 2];     r[15] = c[SC_SW - 3];
         const int sc = oast_score_packed(r, c[0]);
         S[(y0 + ly) * w + x0 + lx] = (uint8_t)sc;
-        if (sc >= BRISK_THRESHOLD) atomicAdd(rc + y0 + ly, 1u);
+        if (sc >= BRISK_THRESHOLD) atomicOr(reinterpret_cast<unsigned*>(&row_hits[ly]) + (lx >> 5), 1u << (lx & 31));   // native 32-bit shared atomic
     }
+    __syncthreads();
+    // one 64-bit word per (layer row, tile column); every word of the tile is written, so the map needs no clearing
+    if (tid < SC_TH && y0 + tid < h)
+        hitmask[((size_t)f * g.rows + L.row0 + y0 + tid) * mask_words + (t % tiles.across[l])] = row_hits[tid];
 }
 
-void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* S, uint32_t* row_count) {
+int score_mask_words(int frame_width) { return (frame_width + SC_TW - 1) / SC_TW; }
+
+void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* S, unsigned long long* hitmask) {
     ScoreTiles tiles;
     int total = 0;
     for (int l = 0; l < N_LAYERS; l++) {
@@ -247,15 +254,41 @@ void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* 
         total += tiles.across[l] * ((g.L[l].h + SC_TH - 1) / SC_TH);
     }
     tiles.first[N_LAYERS] = total;
-    k_scores<<<dim3(total, g.F), dim3(32, 8), 0, st>>>(g, tiles, img, S, row_count);
+    k_scores<<<dim3(total, g.F), dim3(32, 8), 0, st>>>(g, tiles, img, S, hitmask, score_mask_words(g.W));
 }
 
 // ---------------------------------------------------------------------------------------------------
 // ordered candidate list: one warp per (pair, layer row), hits written at the row's scanned offset in x order
 // ---------------------------------------------------------------------------------------------------
+// hits per (pair, layer row) from the hit masks: the input of the exclusive scan that orders the candidate list
+__global__ void k_row_counts(Geom g, const unsigned long long* __restrict__ hitmask, int mask_words, uint32_t* __restrict__ row_count) {
+    const int rowi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total_rows = g.F * g.rows;
+    if (rowi > total_rows) return;
+    if (rowi == total_rows) { row_count[rowi] = 0; return; }
+    const int rr = rowi % g.rows;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < N_LAYERS; k++) l += (rr >= g.L[k].row0);
+    const int words = (g.L[l].w + SC_TW - 1) / SC_TW;
+    const unsigned long long* m = hitmask + (size_t)rowi * mask_words;
+    int n = 0;
+    for (int k = 0; k < words; k++) n += __popcll(m[k]);
+    row_count[rowi] = (uint32_t)n;
+}
+
+void launch_row_counts(cudaStream_t st, const Geom& g, const unsigned long long* hitmask, uint32_t* row_count) {
+    const int n = g.F * g.rows + 1;
+    k_row_counts<<<(n + 255) / 256, 256, 0, st>>>(g, hitmask, score_mask_words(g.W), row_count);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ordered candidate list: one warp per FILL_ROWS (pair, layer) rows; a row's hits are written at its scanned offset in
+// x order, read from the hit masks (one 64-bit word per lane)
+// ---------------------------------------------------------------------------------------------------
 constexpr int FILL_ROWS = 8;      // consecutive (pair, layer) rows per warp
 
-__global__ void k_fill_candidates(Geom g, const uint8_t* __restrict__ S, CandBuf cb) {
+__global__ void k_fill_candidates(Geom g, const unsigned long long* __restrict__ hitmask, int mask_words, CandBuf cb) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int total_rows = g.F * g.rows;
@@ -276,17 +309,12 @@ __global__ void k_fill_candidates(Geom g, const uint8_t* __restrict__ S, CandBuf
         for (int k = 1; k < N_LAYERS; k++) l += (rr >= g.L[k].row0);
         const LayerGeom& L = g.L[l];
         const int y = rr - L.row0;
-        const uint8_t* row = S + L.base + (size_t)f * L.px + y * L.w;
+        const int words = (L.w + SC_TW - 1) / SC_TW;
+        const unsigned long long* m = hitmask + (size_t)rowi * mask_words;
         uint32_t pos = begin;
-        // 4 pixels per lane and step (unaligned 32-bit reads built from aligned loads), hits kept in x order
-        for (int x0 = 0; x0 < L.w && pos < end; x0 += 128) {
-            const int x = x0 + 4 * lane;
-            uint32_t v = x < L.w ? load4(row + x) : 0u;
-            unsigned mask = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (((v >> (8 * k)) & 0xffu) >= (unsigned)BRISK_THRESHOLD && x + k < L.w) mask |= 1u << k;
-            const int cnt = __popc(mask);
+        for (int w0 = 0; w0 < words; w0 += 32) {
+            unsigned long long bits = (w0 + lane < words) ? m[w0 + lane] : 0ull;
+            const int cnt = __popcll(bits);
             int incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -294,25 +322,26 @@ __global__ void k_fill_candidates(Geom g, const uint8_t* __restrict__ S, CandBuf
                 if (lane >= d) incl += nb;
             }
             uint32_t at = pos + (uint32_t)(incl - cnt);
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (mask & (1u << k)) {
-                    if (at < (uint32_t)g.cand_cap) {
-                        cb.xy[at] = (uint32_t)(x + k) | ((uint32_t)y << 16);
-                        cb.meta[at] = ((uint32_t)f << 3) | (uint32_t)l;
-                        cb.flags[at] = 0;
-                    }
-                    at++;
+            const int xbase = (w0 + lane) * SC_TW;
+            while (bits) {
+                const int b = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                if (at < (uint32_t)g.cand_cap) {
+                    cb.xy[at] = (uint32_t)(xbase + b) | ((uint32_t)y << 16);
+                    cb.meta[at] = ((uint32_t)f << 3) | (uint32_t)l;
+                    cb.flags[at] = 0;
                 }
+                at++;
+            }
             pos += (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
         }
     }
 }
 
-void launch_fill_candidates(cudaStream_t st, const Geom& g, const uint8_t* S, CandBuf cb) {
+void launch_fill_candidates(cudaStream_t st, const Geom& g, const unsigned long long* hitmask, CandBuf cb) {
     const int warps = (g.F * g.rows + FILL_ROWS - 1) / FILL_ROWS;
     const int blocks = (warps * 32 + 255) / 256;
-    k_fill_candidates<<<blocks, 256, 0, st>>>(g, S, cb);
+    k_fill_candidates<<<blocks, 256, 0, st>>>(g, hitmask, score_mask_words(g.W), cb);
 }
 
 // ---------------------------------------------------------------------------------------------------
