@@ -37,6 +37,8 @@ struct ProfSpan { int id; cudaEvent_t a, b; };
 
 }  // namespace
 
+enum { DEFAULT_LANES = 4 };
+
 struct mfk_ctx {
     int device = 0, W = 0, H = 0, store_frames = 0, max_pairs = 0;
     int cand_cap_pair = 0, row_cap_pair = 0;
@@ -44,7 +46,8 @@ struct mfk_ctx {
     cudaStream_t copy_stream = nullptr;   // frame-ring uploads, so that H2D of the next frames overlaps the kernels of these
     cudaEvent_t upload_done = nullptr;
     bool upload_pending = false;
-    struct ReadRec { int lo = 0, hi = -1; cudaEvent_t ev[2] = {nullptr, nullptr}; bool on[2] = {false, false}; bool valid = false; };
+    enum { MAX_LANES = 4 };
+    struct ReadRec { int lo = 0, hi = -1; cudaEvent_t ev[MAX_LANES] = {}; bool on[MAX_LANES] = {}; bool valid = false; };
     ReadRec readers[8];                   // which slot ranges recent launch sequences still read
     int reader_next = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -52,8 +55,8 @@ struct mfk_ctx {
     int lw[N_LAYERS], lh[N_LAYERS], rows = 0, pyr_px = 0;
     // device buffers
     uint8_t* store = nullptr;
-    // Two complete sets of per-batch buffers ("lanes"), each with its own streams: consecutive launch sequences
-    // alternate between them, so the latency-bound sparse kernels of one batch run beside the issue-bound dense
+    // Complete sets of per-batch buffers ("lanes"), each with its own streams: consecutive launch sequences
+    // rotate through them, so the latency-bound sparse kernels of one batch run beside the issue-bound dense
     // kernels of the next.  Only the row accumulation (counters, rows_buf, pair_rows) is shared; it is handed from
     // batch to batch through `advanced` events.
     struct Lane {
@@ -62,13 +65,16 @@ struct mfk_ctx {
         int32_t* integral_left = nullptr;
         unsigned long long* hitmask = nullptr;  // detector hits, one 64-bit word per (pair, layer row, 64-column tile)     // per image row: sums left of each 32-column strip
         CandBuf cb{};
+        int32_t* pairs = nullptr;                // this batch's pair descriptions: cur | prev | label, max_pairs each
         uint32_t* scan_scratch = nullptr;
         cudaStream_t stream = nullptr, aux_stream = nullptr;
         cudaEvent_t aux_fork = nullptr, aux_join = nullptr, advanced = nullptr, done = nullptr;
         bool used = false;
     };
-    Lane lane[2];
-    int n_lanes = 2;
+    Lane lane[MAX_LANES];
+    int n_lanes = DEFAULT_LANES, lanes_built = DEFAULT_LANES;
+    bool reset_pending = false;           // mfk_reset_rows is applied in-line by the next launch sequence (or by settle())
+    bool main_wait_pending = false;       // the next launch sequence orders its shared-row part after main_mark
     bool serial = false;
     uint64_t batches = 0;
     int last_lane = 0;
@@ -78,7 +84,6 @@ struct mfk_ctx {
     mfk_row* rows_buf = nullptr;
     size_t row_cap = 0;
     uint32_t* pair_rows = nullptr;
-    int32_t *d_cur = nullptr, *d_prev = nullptr, *d_label = nullptr;
     size_t pair_cap = 0, pairs_queued = 0;
     DeviceTables tb{};
     void* tb_alloc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -191,7 +196,7 @@ int upload_tables(mfk_ctx* c) {
 
 // orders everything queued on the lanes before whatever is queued on the main stream next
 int join_lanes(mfk_ctx* c) {
-    for (int i = 0; i < c->n_lanes; i++) {
+    for (int i = 0; i < c->lanes_built; i++) {
         mfk_ctx::Lane& L = c->lane[i];
         if (!L.used) continue;
         CU(c, cudaEventRecord(L.done, L.stream));
@@ -200,9 +205,20 @@ int join_lanes(mfk_ctx* c) {
     return MFK_OK;
 }
 
+// join_lanes + apply a row reset that no launch sequence has consumed yet: the state every reader of the shared row
+// accumulation (counters, rows_buf, pair_rows) starts from
+int settle(mfk_ctx* c) {
+    { const int rc = join_lanes(c); if (rc != MFK_OK) return rc; }
+    if (c->reset_pending) {
+        CU(c, cudaMemsetAsync(c->counters, 0, 4 * sizeof(uint32_t), c->stream));
+        c->reset_pending = false;
+    }
+    return MFK_OK;
+}
+
 int sync_all(mfk_ctx* c) {
     CU(c, cudaStreamSynchronize(c->copy_stream));
-    for (int i = 0; i < c->n_lanes; i++) {
+    for (int i = 0; i < c->lanes_built; i++) {
         if (c->lane[i].aux_stream) CU(c, cudaStreamSynchronize(c->lane[i].aux_stream));
         if (c->lane[i].stream) CU(c, cudaStreamSynchronize(c->lane[i].stream));
     }
@@ -210,32 +226,29 @@ int sync_all(mfk_ctx* c) {
     return MFK_OK;
 }
 
-int grow_pair_arrays(mfk_ctx* c, size_t need) {
+int grow_pair_rows(mfk_ctx* c, size_t need) {
     if (need <= c->pair_cap) return MFK_OK;
     size_t cap = std::max(need, c->pair_cap * 2);
     cap = std::max<size_t>(cap, 1024);
     { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
-    int32_t *a, *b, *l; uint32_t* pr;
-    CU(c, dalloc(&a, cap)); CU(c, dalloc(&b, cap)); CU(c, dalloc(&l, cap)); CU(c, dalloc(&pr, cap));
-    if (c->pairs_queued) {
-        CU(c, cudaMemcpy(a, c->d_cur, c->pairs_queued * 4, cudaMemcpyDeviceToDevice));
-        CU(c, cudaMemcpy(b, c->d_prev, c->pairs_queued * 4, cudaMemcpyDeviceToDevice));
-        CU(c, cudaMemcpy(l, c->d_label, c->pairs_queued * 4, cudaMemcpyDeviceToDevice));
-        CU(c, cudaMemcpy(pr, c->pair_rows, c->pairs_queued * 4, cudaMemcpyDeviceToDevice));
-    }
-    cudaFree(c->d_cur); cudaFree(c->d_prev); cudaFree(c->d_label); cudaFree(c->pair_rows);
-    c->d_cur = a; c->d_prev = b; c->d_label = l; c->pair_rows = pr; c->pair_cap = cap;
+    uint32_t* pr;
+    CU(c, dalloc(&pr, cap));
+    if (c->pairs_queued) CU(c, cudaMemcpy(pr, c->pair_rows, c->pairs_queued * 4, cudaMemcpyDeviceToDevice));
+    cudaFree(c->pair_rows);
+    c->pair_rows = pr; c->pair_cap = cap;
     return MFK_OK;
 }
 
-// one launch sequence over `F` pairs whose descriptions start at pair index `first`, on the next lane
-int run_batch(mfk_ctx* c, size_t first, int F) {
+// one launch sequence over `F` pairs (host descriptions cur/prev/label), on the next lane; `first` is the index of its
+// first pair among the pairs queued since the last row reset
+int run_batch(mfk_ctx* c, const int32_t* cur, const int32_t* prev, const int32_t* label, size_t first, int F) {
     const Geom g = make_geom(c, F);
-    PairList pl{c->d_cur + first, c->d_prev + first, c->d_label + first};
     const int li = (int)(c->batches % (uint64_t)c->n_lanes);
     mfk_ctx::Lane& L = c->lane[li];
     mfk_ctx::Lane& P = c->lane[c->last_lane];            // lane of the previous batch
     cudaStream_t st = L.stream;
+    PairList pl{L.pairs, L.pairs + c->max_pairs, L.pairs + 2 * (size_t)c->max_pairs};
+    c->launches += launch_set_pairs(st, cur, prev, label, F, pl);
     CU(c, cudaMemsetAsync(L.maps.seen, 0, (size_t)F * g.pyr_px, st));
     CU(c, cudaMemsetAsync(L.cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(L.cb.q_count, 0, 4 * sizeof(uint32_t), st));
@@ -258,6 +271,9 @@ int run_batch(mfk_ctx* c, size_t first, int F) {
     { Span s(c, P_PHASE_B, 1, st);   launch_phase_b(st, g, L.maps, L.cb, c->tb); }
     // from here on the shared row accumulation is touched: wait until the previous batch has advanced it
     if (c->batches > 0 && c->last_lane != li) CU(c, cudaStreamWaitEvent(st, P.advanced, 0));
+    // ... and whatever the caller queued on the main stream before this call (bag-of-words reads of the rows, timers)
+    if (c->main_wait_pending) { CU(c, cudaStreamWaitEvent(st, c->main_mark, 0)); c->main_wait_pending = false; }
+    if (c->reset_pending) { CU(c, cudaMemsetAsync(c->counters, 0, 4 * sizeof(uint32_t), st)); c->reset_pending = false; }
     { Span s(c, P_COMPACT, 5, st);
       launch_keep_flags(st, g, L.cb);
       launch_exclusive_scan(st, L.cb.keep_scan, c->cand_cap, L.cb.live, L.scan_scratch);
@@ -288,13 +304,13 @@ void destroy(mfk_ctx* c) {
         cudaFree(L.cb.row_count); cudaFree(L.cb.xy); cudaFree(L.cb.meta); cudaFree(L.cb.kx); cudaFree(L.cb.ky); cudaFree(L.cb.ksize);
         cudaFree(L.cb.kresp); cudaFree(L.cb.flags); cudaFree(L.cb.scale_idx); cudaFree(L.cb.keep_scan); cudaFree(L.cb.row_src);
         cudaFree(L.cb.pend_count); cudaFree(L.cb.pend_list); cudaFree(L.cb.live);
-        cudaFree(L.cb.q_count); cudaFree(L.cb.q0); cudaFree(L.cb.q1); cudaFree(L.cb.q2); cudaFree(L.cb.q1_up); cudaFree(L.cb.q2_scan); cudaFree(L.scan_scratch);
+        cudaFree(L.cb.q_count); cudaFree(L.cb.q0); cudaFree(L.cb.q1); cudaFree(L.cb.q2); cudaFree(L.cb.q1_up); cudaFree(L.cb.q2_scan); cudaFree(L.scan_scratch); cudaFree(L.pairs);
         for (cudaEvent_t e : {L.aux_fork, L.aux_join, L.advanced, L.done}) if (e) cudaEventDestroy(e);
         if (L.aux_stream) cudaStreamDestroy(L.aux_stream);
         if (L.stream) cudaStreamDestroy(L.stream);
     }
     cudaFree(c->counters);
-    cudaFree(c->rows_buf); cudaFree(c->pair_rows); cudaFree(c->d_cur); cudaFree(c->d_prev); cudaFree(c->d_label);
+    cudaFree(c->rows_buf); cudaFree(c->pair_rows);
     for (void* p : c->tb_alloc) cudaFree(p);
     cudaFree(c->codebook); cudaFree(c->bow_counts); cudaFree(c->bow_tmp);
     if (c->t0) cudaEventDestroy(c->t0);
@@ -357,7 +373,10 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUC(cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->main_mark, cudaEventDisableTiming));
-    for (auto& L : c->lane) {
+    if (const char* e = getenv("MFK_LANES")) c->lanes_built = std::max(1, std::min((int)mfk_ctx::MAX_LANES, atoi(e)));
+    c->n_lanes = c->lanes_built;
+    for (int li = 0; li < c->lanes_built; li++) {
+        mfk_ctx::Lane& L = c->lane[li];
         CUC(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
         CUC(cudaStreamCreateWithFlags(&L.aux_stream, cudaStreamNonBlocking));
         CUC(cudaEventCreateWithFlags(&L.aux_fork, cudaEventDisableTiming));
@@ -388,7 +407,8 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     CUC(cudaMemset(c->counters, 0, 8 * sizeof(uint32_t)));
     // a context that only ever sees one launch sequence per call (max_pairs >= the caller's batches) still gets both
     // lanes: consecutive calls alternate as well
-    for (auto& L : c->lane) {
+    for (int li = 0; li < c->lanes_built; li++) {
+        mfk_ctx::Lane& L = c->lane[li];
         CUC(dalloc(&L.maps.img, F * c->pyr_px + slack));
         CUC(dalloc(&L.maps.S, F * c->pyr_px + slack));
         CUC(dalloc(&L.maps.seen, F * c->pyr_px + slack));
@@ -412,10 +432,11 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
         CUC(cudaMemset(L.cb.live, 0, 2 * sizeof(uint32_t)));
         L.cb.counters = c->counters;
         CUC(dalloc(&L.scan_scratch, scan_n / 2048 + 8));
+        CUC(dalloc(&L.pairs, 3 * F));
     }
     CUC(dalloc(&c->rows_buf, c->row_cap));
     if (upload_tables(c) != MFK_OK) { g_create_error = c->err; destroy(c); return MFK_ERR_CUDA; }
-    if (grow_pair_arrays(c, (size_t)max_pairs) != MFK_OK) { g_create_error = c->err; destroy(c); return MFK_ERR_CUDA; }
+    if (grow_pair_rows(c, (size_t)max_pairs) != MFK_OK) { g_create_error = c->err; destroy(c); return MFK_ERR_CUDA; }
 #undef CUC
     *out = c;
     return MFK_OK;
@@ -443,7 +464,7 @@ int mfk_upload_frames(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_fram
         // slots still being read by queued launch sequences must not be overwritten under them
         for (auto& r : c->readers)
             if (r.valid && r.lo <= slot + run - 1 && r.hi >= slot)
-                for (int k = 0; k < 2; k++) if (r.on[k]) CU(c, cudaStreamWaitEvent(c->copy_stream, r.ev[k], 0));
+                for (int k = 0; k < mfk_ctx::MAX_LANES; k++) if (r.on[k]) CU(c, cudaStreamWaitEvent(c->copy_stream, r.ev[k], 0));
         const uint8_t* src = gray + (size_t)done * stride * c->H;
         if (stride == (size_t)c->W)
             CU(c, cudaMemcpyAsync(c->store + (size_t)slot * px, src, (size_t)run * px, cudaMemcpyHostToDevice, c->copy_stream));
@@ -468,27 +489,24 @@ int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_s
     if (!c || n_pairs < 0 || (n_pairs && (!cur_slot || !prev_slot || !label))) return fail(c, MFK_ERR_ARG, "bad argument to mfk_extract_pairs");
     if (n_pairs == 0) return MFK_OK;
     CU(c, cudaSetDevice(c->device));
-    int rc = grow_pair_arrays(c, c->pairs_queued + (size_t)n_pairs);
+    int rc = grow_pair_rows(c, c->pairs_queued + (size_t)n_pairs);
     if (rc != MFK_OK) return rc;
     const size_t first = c->pairs_queued;
-    // pair descriptions travel on the copy stream, behind any frame uploads; the lanes wait for both through upload_done
-    CU(c, cudaMemcpyAsync(c->d_cur + first, cur_slot, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->copy_stream));
-    CU(c, cudaMemcpyAsync(c->d_prev + first, prev_slot, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->copy_stream));
-    CU(c, cudaMemcpyAsync(c->d_label + first, label, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->copy_stream));
-    CU(c, cudaEventRecord(c->upload_done, c->copy_stream));
     c->upload_pending = false;
-    // ... and for whatever the caller queued on the main stream before this call (row resets, timers)
+    // The lane-private front of a launch sequence (difference image, pyramid, scores, NMS) only waits for the frames;
+    // its shared-row part is additionally ordered after whatever the caller queued on the main stream before this
+    // call (run_batch, main_wait_pending).  So the front of this call overlaps the tail of the previous one.
     CU(c, cudaEventRecord(c->main_mark, c->stream));
-    bool touched[2] = {false, false};
+    c->main_wait_pending = true;
+    bool touched[mfk_ctx::MAX_LANES] = {};
     for (int done = 0; done < n_pairs; done += c->max_pairs) {
         const int F = std::min(c->max_pairs, n_pairs - done);
         const int li = (int)(c->batches % (uint64_t)c->n_lanes);
         if (!touched[li]) {
             CU(c, cudaStreamWaitEvent(c->lane[li].stream, c->upload_done, 0));
-            CU(c, cudaStreamWaitEvent(c->lane[li].stream, c->main_mark, 0));
             touched[li] = true;
         }
-        rc = run_batch(c, first + done, F);
+        rc = run_batch(c, cur_slot + done, prev_slot + done, label + done, first + done, F);
         if (rc != MFK_OK) return rc;
     }
     c->pairs_queued += (size_t)n_pairs;
@@ -501,9 +519,9 @@ int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_s
     mfk_ctx::ReadRec& rec = c->readers[c->reader_next];
     c->reader_next = (c->reader_next + 1) % 8;
     if (rec.valid)          // recycled record: keep its ordering
-        for (int k = 0; k < 2; k++) if (rec.on[k]) CU(c, cudaStreamWaitEvent(c->copy_stream, rec.ev[k], 0));
+        for (int k = 0; k < mfk_ctx::MAX_LANES; k++) if (rec.on[k]) CU(c, cudaStreamWaitEvent(c->copy_stream, rec.ev[k], 0));
     rec.lo = lo; rec.hi = hi; rec.valid = true;
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < mfk_ctx::MAX_LANES; k++) {
         rec.on[k] = touched[k];
         if (touched[k]) CU(c, cudaEventRecord(rec.ev[k], c->lane[k].stream));
     }
@@ -511,7 +529,7 @@ int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_s
 }
 
 static int read_counters(mfk_ctx* c, uint32_t h[4]) {
-    { const int rc = join_lanes(c); if (rc != MFK_OK) return rc; }
+    { const int rc = settle(c); if (rc != MFK_OK) return rc; }
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaMemcpy(h, c->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return MFK_OK;
@@ -520,8 +538,9 @@ static int read_counters(mfk_ctx* c, uint32_t h[4]) {
 int mfk_reset_rows(mfk_ctx* c) {
     if (!c) return MFK_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    { const int rc = join_lanes(c); if (rc != MFK_OK) return rc; }
-    CU(c, cudaMemsetAsync(c->counters, 0, 4 * sizeof(uint32_t), c->stream));
+    // applied by the next launch sequence just before it touches the shared rows (so that its lane-private front may
+    // start under the tail of the previous sequence), or by the next reader of the counters (settle)
+    c->reset_pending = true;
     c->pairs_queued = 0;
     return MFK_OK;
 }
@@ -750,6 +769,8 @@ int mfk_nccl_comm_destroy(void* nccl_comm) {
 int mfk_timer_start(mfk_ctx* c) {
     if (!c) return MFK_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
+    // the lane-private front of the next launch sequence does not wait for the main stream, so start from an idle device
+    { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
     CU(c, cudaEventRecord(c->t0, c->stream));
     return MFK_OK;
 }
@@ -796,7 +817,7 @@ int mfk_set_serial(mfk_ctx* c, int serial) {
     CU(c, cudaSetDevice(c->device));
     { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
     c->serial = serial != 0;
-    c->n_lanes = c->serial ? 1 : 2;
+    c->n_lanes = c->serial ? 1 : c->lanes_built;
     return MFK_OK;
 }
 

@@ -40,7 +40,7 @@ struct CandBuf {                  // ordered candidate list of the batch + per-c
     uint32_t q_cap;
     uint32_t* counters;           // shared by all batches: [0] overflow flags (1 candidates, 2 rows), [1] rows accumulated
                                   // so far, [2] pairs accumulated so far, [3] live candidates of the last batch (copy)
-    uint32_t* live;               // [0] live candidate count of THIS batch (per buffer set)
+    uint32_t* live;               // [0] live candidate count of THIS batch (per buffer set), [1] its overflow flags until k_advance
 };
 
 enum { PEND_CAP = 2048 };         // per (pair, layer); beyond it phase B falls back to an ordered sweep
@@ -56,6 +56,8 @@ struct DeviceTables {             // device copies of mfk::Tables
 };
 
 // --- dense stage ------------------------------------------------------------------------------------
+// pair descriptions travel as kernel parameters (no staging copy, no host stall): 256 per launch; returns launches made
+int launch_set_pairs(cudaStream_t, const int32_t* cur_host, const int32_t* prev_host, const int32_t* label_host, int n, PairList dst);
 void launch_absdiff(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, uint8_t* img);
 void launch_pyramid(cudaStream_t, const Geom&, uint8_t* img);                                  // layers 1..5
 int  score_mask_words(int frame_width);        // 64-bit hit-mask words per (pair, layer row)

@@ -42,6 +42,28 @@ __global__ void k_absdiff(const uint8_t* __restrict__ store, int store_frames, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// pair descriptions: the host arrays ride in the kernel parameter block, 256 pairs (3 KB) per launch
+// ---------------------------------------------------------------------------------------------------
+struct PairChunk { int32_t cur[256], prev[256], label[256]; };
+
+__global__ void k_set_pairs(const __grid_constant__ PairChunk ch, int n, int32_t* cur, int32_t* prev, int32_t* label) {
+    const int i = threadIdx.x;
+    if (i < n) { cur[i] = ch.cur[i]; prev[i] = ch.prev[i]; label[i] = ch.label[i]; }
+}
+
+int launch_set_pairs(cudaStream_t st, const int32_t* cur, const int32_t* prev, const int32_t* label, int n, PairList dst) {
+    int launches = 0;
+    PairChunk ch;
+    for (int done = 0; done < n; done += 256, launches++) {
+        const int m = min(256, n - done);
+        memcpy(ch.cur, cur + done, (size_t)m * 4); memcpy(ch.prev, prev + done, (size_t)m * 4); memcpy(ch.label, label + done, (size_t)m * 4);
+        k_set_pairs<<<1, 256, 0, st>>>(ch, m, const_cast<int32_t*>(dst.cur_slot) + done, const_cast<int32_t*>(dst.prev_slot) + done,
+                                       const_cast<int32_t*>(dst.label) + done);
+    }
+    return launches;
+}
+
 void launch_absdiff(cudaStream_t st, const Geom& g, const uint8_t* store, int store_frames, PairList pl, uint8_t* img) {
     const int px = g.L[0].px;
     const int vec_ok = (px % 16 == 0);     // slots and layer-0 images then start 16-byte aligned
@@ -292,7 +314,7 @@ __global__ void k_fill_candidates(Geom g, const unsigned long long* __restrict__
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int total_rows = g.F * g.rows;
-    if (warp == 0 && lane == 0 && cb.row_count[total_rows] > (uint32_t)g.cand_cap) atomicOr(&cb.counters[0], 1u);
+    if (warp == 0 && lane == 0 && cb.row_count[total_rows] > (uint32_t)g.cand_cap) atomicOr(&cb.live[1], 1u);
     const int row_begin = warp * FILL_ROWS;
     if (row_begin >= total_rows) return;
     const int row_end = min(row_begin + FILL_ROWS, total_rows);

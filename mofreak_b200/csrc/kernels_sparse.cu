@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_pa_test(const __grid_constant__ 
             } else pass = true;
         }
         const uint32_t slot = warp_append(&cb.q_count[0], pass);
-        if (pass) { if (slot < cb.q_cap) cb.q0[slot] = c; else atomicOr(&cb.counters[0], 1u); }
+        if (pass) { if (slot < cb.q_cap) cb.q0[slot] = c; else atomicOr(&cb.live[1], 1u); }
     }
 }
 
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_pa_above(const __grid_constant__
         const uint32_t slot = warp_append(&cb.q_count[1], pass);
         if (pass) {
             if (slot < cb.q_cap) { cb.q1[slot] = c; cb.q1_up[3 * (size_t)slot] = up.max; cb.q1_up[3 * (size_t)slot + 1] = up.dx; cb.q1_up[3 * (size_t)slot + 2] = up.dy; }
-            else atomicOr(&cb.counters[0], 1u);
+            else atomicOr(&cb.live[1], 1u);
         }
     }
 }
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_pa_below(const __grid_constant__
                 float* o = cb.q2_scan + 6 * (size_t)slot;
                 const float* u = cb.q1_up + 3 * (size_t)i;
                 o[0] = u[0]; o[1] = u[1]; o[2] = u[2]; o[3] = dn.max; o[4] = dn.dx; o[5] = dn.dy;
-            } else atomicOr(&cb.counters[0], 1u);
+            } else atomicOr(&cb.live[1], 1u);
         }
     }
 }
@@ -288,6 +288,8 @@ void launch_scatter_rows(cudaStream_t st, const Geom& g, CandBuf cb, uint32_t* p
 __global__ void k_advance(Geom g, CandBuf cb) {
     const uint32_t rows = cb.keep_scan[cb.live[0]];
     const uint32_t have = cb.counters[1];
+    // overflow seen by this batch's lane-private kernels joins the shared flags here, behind any row reset
+    if (cb.live[1]) { cb.counters[0] |= cb.live[1]; cb.live[1] = 0; }
     if (have + rows > (uint32_t)g.row_cap) { cb.counters[0] |= 2u; cb.counters[1] = (uint32_t)g.row_cap; }
     else cb.counters[1] = have + rows;
     cb.counters[2] += (uint32_t)g.F;

@@ -256,5 +256,5 @@ def test_timer_and_profile_hooks():
         ctx.extract_pairs(cur, cur - 5, cur - 1)
         ms = ctx.timer_stop()
         prof = ctx.profile_read()
-        assert ms > 0 and ctx.launch_count() - before == 26
+        assert ms > 0 and ctx.launch_count() - before == 27
         assert prof["scores"][0] == 1 and prof["scores"][1] > 0 and prof["describe"][1] > 0
