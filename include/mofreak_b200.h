@@ -33,6 +33,7 @@ extern "C" {
 #define MFK_ERR_CAPACITY   -3   /* a per-frame candidate/row budget overflowed; recreate with mfk_create_ex */
 #define MFK_ERR_NOMEM      -4
 #define MFK_ERR_STATE      -5   /* call out of order (e.g. fetch before extract) */
+#define MFK_ERR_RANGE      -6   /* a value the device formatter does not cover (see mfk_rows_text) */
 
 #define MFK_FRAME_GAP       5
 
@@ -100,6 +101,26 @@ int  mfk_reset_rows(mfk_ctx* ctx);
  * labels c-1, fetches the rows.  Includes H2D and D2H; this is the end-to-end path. */
 int  mfk_extract_clip(mfk_ctx* ctx, const uint8_t* gray, size_t stride, int n_frames,
                       mfk_row* rows, size_t cap, size_t* n_rows);
+
+/* ---- `.mofreak` text ------------------------------------------------------------------------------- */
+
+/* The rows accumulated since the last fetch/reset as `.mofreak` text in HOST memory, byte for byte what
+ * MoFREAKUtilities::writeMoFREAKFeaturesToFile (MoFREAKUtilities.cpp:691-719) writes for them: per row
+ * "x y frame scale 0 0 a0..a7 m0..m7", each token followed by one space, then '\n', floats as the default
+ * ostream operator<< prints them ("%g").  Formatted on the device; does NOT reset the accumulation.
+ * *n_bytes is the length of the text; if it exceeds cap nothing is copied and MFK_ERR_CAPACITY is returned
+ * (call with text = NULL, cap = 0 to size a buffer).  MFK_ERR_RANGE if a row holds a float outside
+ * 0 | [1e-4, 1e6) (exponent notation; never the case for extracted rows) - format such rows on the host. */
+int  mfk_rows_text(mfk_ctx* ctx, char* text, size_t cap, size_t* n_bytes);
+/* The same for n caller-supplied HOST rows (e.g. a binary row file turned back into text). */
+int  mfk_format_rows(mfk_ctx* ctx, const mfk_row* rows, size_t n, char* text, size_t cap, size_t* n_bytes);
+/* mfk_extract_clip that also returns the clip's `.mofreak` text: one call = one computeMoFREAKFromFile
+ * (MoFREAKUtilities.cpp:374-498 incl. the write at :490-491).  rows may be NULL when only the text is wanted.
+ * If the text or the rows do not fit, *n_bytes / *n_rows hold the sizes needed, MFK_ERR_CAPACITY is returned and
+ * the accumulation is KEPT: read it with mfk_rows_text + mfk_fetch_rows into larger buffers.  Otherwise resets. */
+int  mfk_extract_clip_text(mfk_ctx* ctx, const uint8_t* gray, size_t stride, int n_frames,
+                           char* text, size_t text_cap, size_t* n_bytes,
+                           mfk_row* rows, size_t cap, size_t* n_rows);
 
 /* ---- MIP alone (the MotionInterchangePatterns facade) ------------------------------------------------ */
 

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmofreak_b200.so")
 
-CU_SOURCES = ["context.cu", "kernels_dense.cu", "kernels_sparse.cu", "kernels_desc.cu", "kernels_bow.cu"]
+CU_SOURCES = ["context.cu", "kernels_dense.cu", "kernels_sparse.cu", "kernels_desc.cu", "kernels_bow.cu", "kernels_text.cu"]
 CPP_SOURCES = [os.path.join(CSRC, "tables.cpp"), os.path.join(HERE, "host", "synth.cpp")]
 
 NVCC_FLAGS = [

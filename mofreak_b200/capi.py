@@ -22,7 +22,7 @@ assert ROW_DTYPE.itemsize == 32
 # every symbol include/mofreak_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "mfk_create", "mfk_create_ex", "mfk_destroy", "mfk_last_error", "mfk_sync", "mfk_upload_frames", "mfk_frame_store",
-    "mfk_extract_pairs", "mfk_fetch_rows", "mfk_rows_device", "mfk_reset_rows", "mfk_extract_clip", "mfk_mip_describe",
+    "mfk_extract_pairs", "mfk_fetch_rows", "mfk_rows_device", "mfk_reset_rows", "mfk_extract_clip", "mfk_rows_text", "mfk_format_rows", "mfk_extract_clip_text", "mfk_mip_describe",
     "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram",
     "mfk_allreduce_counts", "mfk_nccl_unique_id", "mfk_nccl_comm_init", "mfk_nccl_comm_destroy", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read",
     "mfk_set_serial", "mfk_launch_count", "mfk_debug_layer", "mfk_debug_keypoints", "mfk_debug_counters", "mfk_synth_clip", "mfk_freak_scale_index", "mfk_version",
@@ -64,6 +64,10 @@ def lib():
     L.mfk_rows_device.argtypes = [p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.mfk_reset_rows.argtypes = [p]
     L.mfk_extract_clip.argtypes = [p, u8p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.mfk_rows_text.argtypes = [p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.mfk_format_rows.argtypes = [p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.mfk_extract_clip_text.argtypes = [p, u8p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                        C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.mfk_mip_describe.argtypes = [p, C.c_int, C.c_int, f32p, C.c_int, u8p]
     L.mfk_bow_set_codebook.argtypes = [p, u8p, C.c_int]
     L.mfk_bow_assign.argtypes = [p, u8p, C.c_size_t, i32p]
@@ -189,6 +193,41 @@ class Context:
         n = C.c_size_t()
         self._check(self._L.mfk_extract_clip(self._h, _ptr(frames), self.width, frames.shape[0], _ptr(rows), cap, C.byref(n)))
         return rows[:n.value].copy()
+
+    # --- `.mofreak` text, formatted on the device ---
+    def rows_text(self):
+        """Text of the accumulated rows (bytes); the accumulation is kept."""
+        n = C.c_size_t()
+        rc = self._L.mfk_rows_text(self._h, None, 0, C.byref(n))
+        if rc != 0 and not (rc == -3 and n.value > 0):
+            self._check(rc)
+        buf = np.empty(max(1, n.value), np.uint8)
+        self._check(self._L.mfk_rows_text(self._h, _ptr(buf), buf.size, C.byref(n)))
+        return buf[:n.value].tobytes()
+
+    def rows_text_raw(self, host_ptr, cap):
+        n = C.c_size_t()
+        self._check(self._L.mfk_rows_text(self._h, C.c_void_p(host_ptr), cap, C.byref(n)))
+        return n.value
+
+    def format_rows(self, rows):
+        rows = np.ascontiguousarray(rows, ROW_DTYPE)
+        buf = np.empty(max(1, rows.size * 128), np.uint8)
+        n = C.c_size_t()
+        self._check(self._L.mfk_format_rows(self._h, _ptr(rows), rows.size, _ptr(buf), buf.size, C.byref(n)))
+        return buf[:n.value].tobytes()
+
+    def extract_clip_text(self, frames, want_rows=True, cap=None):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        assert frames.ndim == 3 and frames.shape[1:] == (self.height, self.width)
+        if cap is None:
+            cap = max(1024, frames.shape[0] * 4096)
+        rows = np.empty(cap, ROW_DTYPE) if want_rows else None
+        text = np.empty(cap * 128, np.uint8)
+        n, nb = C.c_size_t(), C.c_size_t()
+        self._check(self._L.mfk_extract_clip_text(self._h, _ptr(frames), self.width, frames.shape[0], _ptr(text), text.size, C.byref(nb),
+                                                  _ptr(rows) if want_rows else None, cap if want_rows else 0, C.byref(n)))
+        return text[:nb.value].tobytes(), (rows[:n.value].copy() if want_rows else n.value)
 
     def mip_describe(self, cur_slot, prev_slot, kp_xys):
         kp = np.ascontiguousarray(kp_xys, np.float32).reshape(-1, 3)

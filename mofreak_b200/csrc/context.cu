@@ -29,9 +29,9 @@ namespace {
 thread_local std::string g_create_error;
 
 enum ProfId { P_ABSDIFF, P_PYRAMID, P_SCORES, P_SCAN, P_FILL, P_INTEGRAL, P_PHASE_A, P_PHASE_B, P_COMPACT, P_DESCRIBE,
-              P_BOW, P_MIP, P_COUNT };
+              P_BOW, P_MIP, P_TEXT, P_COUNT };
 const char* const kProfNames[P_COUNT] = {"absdiff", "pyramid", "scores", "scan", "fill_candidates", "integral", "phase_a",
-                                         "phase_b", "compact", "describe", "bow_assign", "mip_only"};
+                                         "phase_b", "compact", "describe", "bow_assign", "mip_only", "text"};
 // kernels launched per call of each launcher family (for gpu_launches accounting)
 struct ProfSpan { int id; cudaEvent_t a, b; };
 
@@ -93,6 +93,13 @@ struct mfk_ctx {
     int bow_counts_cap = 0;
     void* bow_tmp = nullptr;
     size_t bow_tmp_bytes = 0;
+    // `.mofreak` text formatting: line lengths/offsets (+ scan scratch, + flag word), the text itself, staged rows
+    uint32_t* text_off = nullptr;
+    size_t text_off_cap = 0;
+    char* text_buf = nullptr;
+    size_t text_buf_cap = 0;
+    mfk_row* text_rows = nullptr;
+    size_t text_rows_cap = 0;
     // last batch (debug access)
     Geom last{};
     bool have_last = false;
@@ -313,6 +320,7 @@ void destroy(mfk_ctx* c) {
     cudaFree(c->rows_buf); cudaFree(c->pair_rows);
     for (void* p : c->tb_alloc) cudaFree(p);
     cudaFree(c->codebook); cudaFree(c->bow_counts); cudaFree(c->bow_tmp);
+    cudaFree(c->text_off); cudaFree(c->text_buf); cudaFree(c->text_rows);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->upload_done) cudaEventDestroy(c->upload_done);
@@ -329,6 +337,47 @@ int ensure_bow_tmp(mfk_ctx* c, size_t bytes) {
     cudaFree(c->bow_tmp); c->bow_tmp = nullptr; c->bow_tmp_bytes = 0;
     CU(c, cudaMalloc(&c->bow_tmp, bytes));
     c->bow_tmp_bytes = bytes;
+    return MFK_OK;
+}
+
+// `.mofreak` text of n device rows on the main stream, copied to the caller's HOST buffer
+int format_device_rows(mfk_ctx* c, const mfk_row* d_rows, size_t n, char* text, size_t cap, size_t* n_bytes) {
+    if (n_bytes) *n_bytes = 0;
+    if (n == 0) return MFK_OK;
+    if (n > 0xfffffff0u / TEXT_ROW_MAX) return fail(c, MFK_ERR_ARG, "%zu rows exceed the 4 GiB text limit of one call", n);
+    // layout of text_off: [0, n] lengths -> offsets (slot n = total) | scan scratch | flag word
+    const size_t scratch_words = (n + 1) / 2048 + 8;
+    const size_t need = n + 1 + scratch_words + 1;
+    if (need > c->text_off_cap) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->text_off); c->text_off = nullptr; c->text_off_cap = 0;
+        CU(c, dalloc(&c->text_off, need + need / 4));
+        c->text_off_cap = need + need / 4;
+    }
+    uint32_t* off = c->text_off;
+    uint32_t* scratch = off + n + 1;
+    uint32_t* flags = scratch + scratch_words;
+    CU(c, cudaMemsetAsync(flags, 0, 4, c->stream));
+    uint32_t h[2] = {0, 0};      // total bytes, flags
+    { Span s(c, P_TEXT, 4);
+      launch_text_lengths(c->stream, d_rows, (uint32_t)n, off, flags);
+      launch_exclusive_scan(c->stream, off, (int)(n + 1), nullptr, scratch); }
+    CU(c, cudaMemcpyAsync(&h[0], off + n, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(&h[1], flags, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (h[1]) return fail(c, MFK_ERR_RANGE, "a row holds a float that \"%%g\" prints in exponent notation; format these rows on the host");
+    if (n_bytes) *n_bytes = h[0];
+    if (h[0] > cap || !text) return fail(c, MFK_ERR_CAPACITY, "%u bytes of text do not fit the caller's buffer of %zu", h[0], cap);
+    if (h[0] > c->text_buf_cap) {
+        cudaFree(c->text_buf); c->text_buf = nullptr; c->text_buf_cap = 0;
+        const size_t want = (size_t)h[0] + h[0] / 4 + 256;
+        CU(c, cudaMalloc((void**)&c->text_buf, want));
+        c->text_buf_cap = want;
+    }
+    { Span s(c, P_TEXT, 1); launch_text_write(c->stream, d_rows, (uint32_t)n, off, c->text_buf); }
+    CU(c, cudaMemcpyAsync(text, c->text_buf, h[0], cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaGetLastError());
     return MFK_OK;
 }
 
@@ -581,9 +630,68 @@ int mfk_fetch_rows(mfk_ctx* c, mfk_row* rows, size_t cap, size_t* n_rows, uint32
     return MFK_OK;
 }
 
+int mfk_rows_text(mfk_ctx* c, char* text, size_t cap, size_t* n_bytes) {
+    if (!c || (cap && !text)) return fail(c, MFK_ERR_ARG, "bad argument to mfk_rows_text");
+    CU(c, cudaSetDevice(c->device));
+    uint32_t h[4];
+    int rc = read_counters(c, h);
+    if (rc != MFK_OK) return rc;
+    if (h[0]) return fail(c, MFK_ERR_CAPACITY, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
+                          (h[0] & 1) ? "candidates " : "", (h[0] & 2) ? "rows" : "");
+    return format_device_rows(c, c->rows_buf, h[1], text, cap, n_bytes);
+}
+
+int mfk_format_rows(mfk_ctx* c, const mfk_row* rows, size_t n, char* text, size_t cap, size_t* n_bytes) {
+    if (!c || (n && !rows) || (cap && !text)) return fail(c, MFK_ERR_ARG, "bad argument to mfk_format_rows");
+    CU(c, cudaSetDevice(c->device));
+    if (n > c->text_rows_cap) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->text_rows); c->text_rows = nullptr; c->text_rows_cap = 0;
+        CU(c, dalloc(&c->text_rows, n + n / 4));
+        c->text_rows_cap = n + n / 4;
+    }
+    if (n) CU(c, cudaMemcpyAsync(c->text_rows, rows, n * sizeof(mfk_row), cudaMemcpyHostToDevice, c->stream));
+    return format_device_rows(c, c->text_rows, n, text, cap, n_bytes);
+}
+
+static int enqueue_clip(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_frames);
+
 int mfk_extract_clip(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_frames, mfk_row* rows, size_t cap, size_t* n_rows) {
     if (!c || !gray || n_frames < 0) return fail(c, MFK_ERR_ARG, "bad argument to mfk_extract_clip");
     if (n_rows) *n_rows = 0;
+    const int rc = enqueue_clip(c, gray, stride, n_frames);
+    if (rc != MFK_OK) return rc;
+    return mfk_fetch_rows(c, rows, cap, n_rows, nullptr, 0);
+}
+
+int mfk_extract_clip_text(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_frames, char* text, size_t text_cap, size_t* n_bytes,
+                          mfk_row* rows, size_t cap, size_t* n_rows) {
+    if (!c || !gray || n_frames < 0 || (text_cap && !text)) return fail(c, MFK_ERR_ARG, "bad argument to mfk_extract_clip_text");
+    if (n_rows) *n_rows = 0;
+    if (n_bytes) *n_bytes = 0;
+    int rc = enqueue_clip(c, gray, stride, n_frames);
+    if (rc != MFK_OK) return rc;
+    uint32_t h[4];
+    rc = read_counters(c, h);
+    if (rc != MFK_OK) return rc;
+    if (n_rows) *n_rows = h[1];
+    if (h[0]) {
+        mfk_reset_rows(c);
+        return fail(c, MFK_ERR_CAPACITY, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
+                    (h[0] & 1) ? "candidates " : "", (h[0] & 2) ? "rows" : "");
+    }
+    const int rc_text = format_device_rows(c, c->rows_buf, h[1], text, text_cap, n_bytes);
+    if (rc_text != MFK_OK && rc_text != MFK_ERR_RANGE) return rc_text;       // a text buffer too small keeps the accumulation
+    if (rows && h[1] > cap)
+        return fail(c, MFK_ERR_CAPACITY, "%u rows do not fit the caller's buffer of %zu (accumulation kept)", h[1], cap);
+    const std::string text_err = c->err;
+    rc = rows ? mfk_fetch_rows(c, rows, cap, n_rows, nullptr, 0) : mfk_reset_rows(c);
+    if (rc != MFK_OK) return rc;
+    if (rc_text != MFK_OK) c->err = text_err;
+    return rc_text;
+}
+
+static int enqueue_clip(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_frames) {
     int rc = mfk_reset_rows(c);
     if (rc != MFK_OK) return rc;
     if (n_frames <= MFK_FRAME_GAP) return MFK_OK;
@@ -606,7 +714,7 @@ int mfk_extract_clip(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_frame
         if (rc != MFK_OK) return rc;
         next = last + 1;      // the next upload reuses slots; it is ordered after these kernels by the stream
     }
-    return mfk_fetch_rows(c, rows, cap, n_rows, nullptr, 0);
+    return MFK_OK;
 }
 
 int mfk_mip_describe(mfk_ctx* c, int cur_slot, int prev_slot, const float* kp_xys, int n, uint8_t* motion) {

@@ -42,4 +42,6 @@ enum {
     ST_KEYPOINT = 16,   // BRISK keypoint (before FREAK's border filter)
 };
 
+constexpr int TEXT_ROW_MAX = 128;     // upper bound of one `.mofreak` text line (text_device.cuh)
+
 }  // namespace mfk

@@ -84,4 +84,9 @@ void launch_mip_only(cudaStream_t, int W, int H, const uint8_t* cur, const uint8
 void launch_bow_assign(cudaStream_t, const uint8_t* desc, size_t stride_bytes, size_t n, const uint8_t* codebook, int K,
                        int32_t* idx, uint32_t* counts /*nullable*/);
 
+// `.mofreak` text (kernels_text.cu): line lengths into len[0..n] (slot n = 0, the scan makes it the total; flags |= 1 if a float
+// needs exponent notation), then the lines at their scanned offsets
+void launch_text_lengths(cudaStream_t, const void* rows, uint32_t n, uint32_t* len, uint32_t* flags);
+void launch_text_write(cudaStream_t, const void* rows, uint32_t n, const uint32_t* off, char* text);
+
 }  // namespace mfk

@@ -82,7 +82,7 @@ void formatMoFREAKRow(std::string& out, float x, float y, int frame, float scale
     out += '\n';
 }
 
-MoFREAKUtilities::MoFREAKUtilities(int dset) : current_action(0), dataset(dset), device_(0), ctx_(nullptr), ctx_w_(0), ctx_h_(0), budget_scale_(1) {}
+MoFREAKUtilities::MoFREAKUtilities(int dset) : current_action(0), dataset(dset), device_(0), ctx_(nullptr), ctx_w_(0), ctx_h_(0), budget_scale_(1), rows_per_frame_hint_(1024) {}
 
 MoFREAKUtilities::~MoFREAKUtilities() { mfk_destroy(ctx_); }
 
@@ -122,38 +122,60 @@ void MoFREAKUtilities::computeMoFREAKFromFile(std::string video_filename, std::s
 void MoFREAKUtilities::computeMoFREAKFromFrames(const uint8_t* gray, int width, int height, int n_frames, const std::string& name_for_metadata,
                                                 const std::string& mofreak_filename, bool clear_features_after_computation) {
     ensureContext(width, height);
-    size_t cap = (size_t)std::max(1, n_frames) * 2048, n = 0;
+    // Rows AND their `.mofreak` text come back from the device (mfk_extract_clip_text): the reference's 22 ostream
+    // tokens per row (:691-719) would otherwise cost far more host time than the whole extraction costs the GPU.
+    size_t cap = (size_t)std::max(1, n_frames) * rows_per_frame_hint_, n = 0, n_text = 0;
     int rc;
     for (;;) {
         last_rows_.resize(cap);
-        rc = mfk_extract_clip(ctx_, gray, (size_t)width, n_frames, last_rows_.data(), cap, &n);
-        if (rc == MFK_ERR_CAPACITY && n > cap) { cap = n; continue; }     // the caller's buffer was too small: retry with the exact size
+        last_text_.resize(cap * 96);
+        rc = mfk_extract_clip_text(ctx_, gray, (size_t)width, n_frames, &last_text_[0], last_text_.size(), &n_text, last_rows_.data(), cap, &n);
+        if (rc == MFK_ERR_CAPACITY && (n > cap || n_text > last_text_.size())) {
+            // a buffer of ours was too small; the device kept the accumulation, so read it again with exact sizes
+            last_rows_.resize(n);
+            last_text_.resize(std::max<size_t>(n_text, 1));
+            rc = mfk_rows_text(ctx_, &last_text_[0], last_text_.size(), &n_text);
+            const int rc_rows = mfk_fetch_rows(ctx_, last_rows_.data(), n, &n, nullptr, 0);
+            if (rc == MFK_OK || rc == MFK_ERR_RANGE) { if (rc_rows != MFK_OK) rc = rc_rows; }
+            break;
+        }
         if (rc == MFK_ERR_CAPACITY && budget_scale_ < 64) {                 // a device-side budget overflowed (very busy frames):
             ensureContext(width, height, budget_scale_ * 4);                // the reference has no such limit, so grow and redo
             continue;
         }
         break;
     }
-    if (rc != MFK_OK) die(std::string("mofreak_b200: ") + mfk_last_error(ctx_));
+    const bool text_on_host = rc == MFK_ERR_RANGE;                          // a float "%g" prints in exponent notation: never for extracted rows
+    if (rc != MFK_OK && !text_on_host) die(std::string("mofreak_b200: ") + mfk_last_error(ctx_));
     last_rows_.resize(n);
+    last_text_.resize(text_on_host ? 0 : n_text);
 
     // gather metadata once per video (the reference re-parses the file name per keypoint, :468-469)
     int action = 0, person = 0, video_number = 0;
     readMetadata(name_for_metadata, action, video_number, person);
-    for (const mfk_row& r : last_rows_) {
-        MoFREAKFeature ftr(NUMBER_OF_BYTES_FOR_MOTION, NUMBER_OF_BYTES_FOR_APPEARANCE);
-        ftr.frame_number = r.frame;
-        ftr.scale = r.scale;
-        ftr.x = r.x;
-        ftr.y = r.y;
-        for (int i = 0; i < NUMBER_OF_BYTES_FOR_APPEARANCE; ++i) ftr.appearance[i] = r.appearance[i];
-        for (int i = 0; i < NUMBER_OF_BYTES_FOR_MOTION; ++i) ftr.motion[i] = r.motion[i];
-        ftr.action = action; ftr.video_number = video_number; ftr.person = person;
-        ftr.motion_x = 0; ftr.motion_y = 0;
-        features.push_back(ftr);
+    const bool had_features = !features.empty();
+    // the deque is only materialised when somebody can see it: the reference's callers pass clear = true (main.cpp:878, 918)
+    if (!clear_features_after_computation || had_features || text_on_host) {
+        for (const mfk_row& r : last_rows_) {
+            MoFREAKFeature ftr(NUMBER_OF_BYTES_FOR_MOTION, NUMBER_OF_BYTES_FOR_APPEARANCE);
+            ftr.frame_number = r.frame;
+            ftr.scale = r.scale;
+            ftr.x = r.x;
+            ftr.y = r.y;
+            for (int i = 0; i < NUMBER_OF_BYTES_FOR_APPEARANCE; ++i) ftr.appearance[i] = r.appearance[i];
+            for (int i = 0; i < NUMBER_OF_BYTES_FOR_MOTION; ++i) ftr.motion[i] = r.motion[i];
+            ftr.action = action; ftr.video_number = video_number; ftr.person = person;
+            ftr.motion_x = 0; ftr.motion_y = 0;
+            features.push_back(ftr);
+        }
     }
     std::cout << "Writing this mofreak file: " << mofreak_filename << std::endl;
-    writeMoFREAKFeaturesToFile(mofreak_filename);
+    if (had_features || text_on_host) writeMoFREAKFeaturesToFile(mofreak_filename);      // earlier features are written too, as in the reference
+    else {
+        std::ofstream f(mofreak_filename, std::ios::binary);
+        f.write(last_text_.data(), (std::streamsize)last_text_.size());
+        f.close();
+    }
     if (clear_features_after_computation) features.clear();
 }
 

@@ -73,6 +73,9 @@ public:
     void setDevice(int device) { device_ = device; }
     // rows of the last computeMoFREAKFrom* call in the binary layout of the C ABI
     const std::vector<mfk_row>& lastRows() const { return last_rows_; }
+    const std::string& lastText() const { return last_text_; }
+    // initial size of the host row/text buffers (rows per frame); too small only costs one more read of the device rows
+    void setRowsPerFrameHint(size_t rows) { rows_per_frame_hint_ = rows ? rows : 1; }
 
 private:
     void readMetadata(std::string filename, int& action, int& video_number, int& person);
@@ -86,6 +89,8 @@ private:
     int ctx_w_, ctx_h_;
     int budget_scale_;     // 1, 4, 16, ... multiplier on the default per-pair candidate/row budgets
     std::vector<mfk_row> last_rows_;
+    size_t rows_per_frame_hint_;
+    std::string last_text_;                  // `.mofreak` text of the last clip as formatted on the device
 };
 
 // .mofreak text exactly as writeMoFREAKFeaturesToFile prints it (MoFREAKUtilities.cpp:691-719)

@@ -21,6 +21,15 @@ long mfkh_compute_mofreak_from_file(int dset, const char* video, const char* mof
     return (long)u.getMoFREAKFeatures().size();
 }
 
+// the call the reference's drivers make (clear = true, main.cpp:878, 918): the file comes straight from the device-formatted
+// text and no feature deque is built; rows_hint sizes the first host buffers (1 forces the re-read path)
+long mfkh_compute_mofreak_clear(int dset, const char* video, const char* mofreak, long rows_hint) {
+    MoFREAKUtilities u(dset);
+    if (rows_hint > 0) u.setRowsPerFrameHint((size_t)rows_hint);
+    u.computeMoFREAKFromFile(video, mofreak, true);
+    return u.getMoFREAKFeatures().empty() ? (long)u.lastRows().size() : -1;
+}
+
 // reads a .mofreak file with the host reader and writes it back (round trip of reader + writer, in file order)
 long mfkh_rewrite_mofreak(const char* in, const char* out) {
     MoFREAKUtilities u(MoFREAKUtilities::KTH);

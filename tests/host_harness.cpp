@@ -31,6 +31,7 @@ static inline uint32_t __vimax3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
 #include "../mofreak_b200/csrc/dense_device.cuh"
 #include "../mofreak_b200/csrc/sparse_device.cuh"
 #include "../mofreak_b200/csrc/desc_device.cuh"
+#include "../mofreak_b200/csrc/text_device.cuh"
 
 using namespace mfk;
 
@@ -268,3 +269,29 @@ long hh_atan2f_sweep(int grid, long random_pairs, unsigned seed) {
 }
 
 }  // extern "C"
+
+// `.mofreak` text of n rows (text_device.cuh, the code k_text_lengths / k_text_write run): returns the length, or -(row + 1)
+// for the first row that needs exponent notation.  `count_only` exercises the counting sink of the first pass.
+extern "C" long hh_format_rows(const void* rows, long n, char* out, int count_only) {
+    const TextRow* r = (const TextRow*)rows;
+    long total = 0;
+    for (long i = 0; i < n; i++) {
+        CountSink cs;
+        if (!put_row(cs, r[i])) return -(i + 1);
+        if (cs.n > TEXT_ROW_MAX) return -(i + 1);
+        if (!count_only) {
+            BufSink bs(out + total);
+            put_row(bs, r[i]);
+            if (bs.n != cs.n) return -(i + 1);
+        }
+        total += cs.n;
+    }
+    return total;
+}
+
+// "%g" of one float through the device formatter; returns the length or -1
+extern "C" int hh_format_float(float v, char* out) {
+    BufSink bs(out);
+    if (!put_float_g(bs, v)) return -1;
+    return bs.n;
+}

@@ -22,6 +22,8 @@ def host():
     L = C.CDLL(path)
     L.mfkh_compute_mofreak_from_file.restype = C.c_long
     L.mfkh_rewrite_mofreak.restype = C.c_long
+    L.mfkh_compute_mofreak_clear.restype = C.c_long
+    L.mfkh_compute_mofreak_clear.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_long]
     return L
 
 
@@ -76,6 +78,20 @@ def test_compute_mofreak_from_file_writes_the_golden_file(host, tmp_path, name):
     n = host.mfkh_compute_mofreak_from_file(0, str(video).encode(), str(out).encode())
     assert n == c["rows"]
     assert out.read_text() == util.golden_text(name)          # the .mofreak file is byte-identical
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows_hint", [0, 1])
+def test_clear_after_computation_writes_device_text_without_building_features(host, tmp_path, rows_hint):
+    name = "ucf_320x240x12_seed3"
+    c = util.golden_cases()[name]
+    clip = mofreak_b200.synth_clip(c["width"], c["height"], c["frames"], c["seed"])
+    video = tmp_path / "v.y8"; out = tmp_path / "v.mofreak"
+    host.mfkh_write_gray_video(str(video).encode(), clip.ctypes.data_as(C.c_void_p), c["width"], c["height"], c["frames"])
+    # rows_hint = 1: the first host buffers are too small, the device keeps the rows and they are read again
+    n = host.mfkh_compute_mofreak_clear(3, str(video).encode(), str(out).encode(), rows_hint)
+    assert n == c["rows"]
+    assert out.read_text() == util.golden_text(name)
 
 
 @pytest.mark.gpu
