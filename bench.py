@@ -257,6 +257,15 @@ def run_ours(args):
         ctx.bow_histogram_rows()
     ms_bow = ctx.timer_stop() / max(3, args.steps)
 
+    # ---- `.mofreak` text of the step's rows, formatted on the device and copied to pinned host memory ----
+    text_host = torch.empty((int(n_rows_step) * 100 + 4096,), dtype=torch.uint8, pin_memory=True)
+    step_resident(); ctx.sync()
+    text_bytes = ctx.rows_text_raw(text_host.data_ptr(), text_host.numel())
+    t0 = time.perf_counter()
+    for _ in range(max(3, args.steps)):
+        ctx.rows_text_raw(text_host.data_ptr(), text_host.numel())
+    ms_text = (time.perf_counter() - t0) * 1e3 / max(3, args.steps)
+
     # ---- end to end: host buffers in, host rows out, copies inside the timed region ----
     # chunks of whole streams: the upload of chunk k+1 (copy stream) overlaps the kernels of chunk k
     chunk_streams = max(1, min(STREAMS, MAX_PAIRS // PAIRS_PER_STREAM))
@@ -356,12 +365,16 @@ def run_ours(args):
                          "whole_path_frac": (algorithmic_bytes_per_frame(rows_per_frame) * value / world) / 1e9 / peak},
             "kernel_ms_per_step": {k: v[1] / args.steps for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])},
             "kernel_accounting": "CUDA events per kernel family over %d serialised steps of the same run (%.2f ms/step serialised vs "
-                                 "%.2f ms/step with two launch sequences overlapping)" % (args.steps, ms_serial / args.steps, ms_res / args.steps),
+                                 "%.2f ms/step with four launch sequences in flight)" % (args.steps, ms_serial / args.steps, ms_res / args.steps),
             "clocks": clocks,
             "bow": {"codebook_words": 600, "descriptors_per_call": int(n_rows_step), "ms_per_call": ms_bow,
                     "descriptors_per_sec": n_rows_step / (ms_bow / 1e3), "popc64_per_sec": n_rows_step * 1200 / (ms_bow / 1e3),
                     "note": "mfk_bow_histogram_rows on the device-resident rows of one step incl. the 2.4 KB count read-back; "
                             "integer-pipe bound (2 XOR + 2 POPC.64 per codeword), HBM traffic 32 B per descriptor"},
+            "text": {"rows_per_call": int(n_rows_step), "bytes_per_call": int(text_bytes), "ms_per_call": ms_text,
+                     "rows_per_sec": n_rows_step / (ms_text / 1e3),
+                     "note": "mfk_rows_text: `.mofreak` lines of one step's device-resident rows (exact %g in integer arithmetic), "
+                             "incl. the D2H copy of the text to pinned memory; host clock"},
         }
         if cpu:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"]}
