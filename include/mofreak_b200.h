@@ -168,6 +168,11 @@ int  mfk_timer_stop(mfk_ctx* ctx, float* elapsed_ms);   /* syncs */
 typedef struct mfk_prof_entry { const char* name; uint32_t launches; float total_ms; } mfk_prof_entry;
 int  mfk_profile_enable(mfk_ctx* ctx, int enable);
 int  mfk_profile_read(mfk_ctx* ctx, mfk_prof_entry* entries, int cap, int* n_entries);
+/* Timeline of the spans recorded since mfk_profile_enable and not yet consumed by mfk_profile_read: one entry per
+ * launcher call (kernel family), start/end in device ms relative to the last mfk_timer_start.  With the lanes overlapping
+ * this is the Gantt chart of the launch sequences (the reference has no tracing).  Syncs. */
+typedef struct mfk_span { const char* name; float start_ms, end_ms; } mfk_span;
+int  mfk_profile_timeline(mfk_ctx* ctx, mfk_span* spans, int cap, int* n_spans);
 /* serial != 0: consecutive launch sequences no longer overlap (one buffer set, the integral image on the main stream).
  * Throughput runs leave this off; the per-kernel accounting of mfk_profile_* is only a kernel's own time when it is on. */
 int  mfk_set_serial(mfk_ctx* ctx, int serial);

@@ -24,9 +24,13 @@ SYMBOLS = [
     "mfk_create", "mfk_create_ex", "mfk_destroy", "mfk_last_error", "mfk_sync", "mfk_upload_frames", "mfk_frame_store",
     "mfk_extract_pairs", "mfk_fetch_rows", "mfk_rows_device", "mfk_reset_rows", "mfk_extract_clip", "mfk_rows_text", "mfk_format_rows", "mfk_extract_clip_text", "mfk_mip_describe",
     "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram",
-    "mfk_allreduce_counts", "mfk_nccl_unique_id", "mfk_nccl_comm_init", "mfk_nccl_comm_destroy", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read",
+    "mfk_allreduce_counts", "mfk_nccl_unique_id", "mfk_nccl_comm_init", "mfk_nccl_comm_destroy", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read", "mfk_profile_timeline",
     "mfk_set_serial", "mfk_launch_count", "mfk_debug_layer", "mfk_debug_keypoints", "mfk_debug_counters", "mfk_synth_clip", "mfk_freak_scale_index", "mfk_version",
 ]
+
+
+class _Span(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("start_ms", C.c_float), ("end_ms", C.c_float)]
 
 
 class MofreakError(RuntimeError):
@@ -82,6 +86,7 @@ def lib():
     L.mfk_timer_stop.argtypes = [p, C.POINTER(C.c_float)]
     L.mfk_profile_enable.argtypes = [p, C.c_int]
     L.mfk_profile_read.argtypes = [p, C.POINTER(_ProfEntry), C.c_int, C.POINTER(C.c_int)]
+    L.mfk_profile_timeline.argtypes = [p, C.POINTER(_Span), C.c_int, C.POINTER(C.c_int)]
     L.mfk_set_serial.argtypes = [p, C.c_int]
     L.mfk_launch_count.argtypes = [p]; L.mfk_launch_count.restype = C.c_uint64
     L.mfk_debug_layer.argtypes = [p, C.c_int, C.c_int, C.c_int, u8p, C.POINTER(C.c_int)]
@@ -299,6 +304,13 @@ class Context:
         n = C.c_int()
         self._check(self._L.mfk_profile_read(self._h, ent, 16, C.byref(n)))
         return {ent[i].name.decode(): (ent[i].launches, ent[i].total_ms) for i in range(n.value)}
+
+    def profile_timeline(self, cap=65536):
+        """[(family, start_ms, end_ms)] of the recorded spans, relative to the last timer_start; call before profile_read."""
+        ent = (_Span * cap)()
+        n = C.c_int()
+        self._check(self._L.mfk_profile_timeline(self._h, ent, cap, C.byref(n)))
+        return [(ent[i].name.decode(), ent[i].start_ms, ent[i].end_ms) for i in range(n.value)]
 
     def set_serial(self, on=True):
         self._check(self._L.mfk_set_serial(self._h, 1 if on else 0))

@@ -70,6 +70,7 @@ struct mfk_ctx {
         cudaStream_t stream = nullptr, aux_stream = nullptr;
         cudaEvent_t aux_fork = nullptr, aux_join = nullptr, advanced = nullptr, done = nullptr;
         bool used = false;
+        int seen_F = -1;                         // batch size the `seen` map was last cleared for (layer bases depend on it)
     };
     Lane lane[MAX_LANES];
     int n_lanes = DEFAULT_LANES, lanes_built = DEFAULT_LANES;
@@ -256,7 +257,10 @@ int run_batch(mfk_ctx* c, const int32_t* cur, const int32_t* prev, const int32_t
     cudaStream_t st = L.stream;
     PairList pl{L.pairs, L.pairs + c->max_pairs, L.pairs + 2 * (size_t)c->max_pairs};
     c->launches += launch_set_pairs(st, cur, prev, label, F, pl);
-    CU(c, cudaMemsetAsync(L.maps.seen, 0, (size_t)F * g.pyr_px, st));
+    // write-back marks only ever land on layers 1..5 (they come from scans issued from the layer below), so layer 0's
+    // share of the map stays zero as long as the lane keeps its geometry
+    if (L.seen_F == F) CU(c, cudaMemsetAsync(L.maps.seen + g.L[1].base, 0, (size_t)F * g.pyr_px - g.L[1].base, st));
+    else { CU(c, cudaMemsetAsync(L.maps.seen, 0, (size_t)c->max_pairs * c->pyr_px, st)); L.seen_F = F; }
     CU(c, cudaMemsetAsync(L.cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(L.cb.q_count, 0, 4 * sizeof(uint32_t), st));
     { Span s(c, P_ABSDIFF, 1, st);   launch_absdiff(st, g, c->store, c->store_frames, pl, L.maps.img); }
@@ -276,20 +280,24 @@ int run_batch(mfk_ctx* c, const int32_t* cur, const int32_t* prev, const int32_t
     { Span s(c, P_FILL, 1, st);      launch_fill_candidates(st, g, L.hitmask, L.cb); }
     { Span s(c, P_PHASE_A, 4, st);   launch_phase_a(st, g, L.maps, L.cb, c->tb); }
     { Span s(c, P_PHASE_B, 1, st);   launch_phase_b(st, g, L.maps, L.cb, c->tb); }
-    // from here on the shared row accumulation is touched: wait until the previous batch has advanced it
+    // From here on batches run one after the other.  Only k_advance (this batch's base in the shared row accumulation, the
+    // counters) needs that; the second compaction and the descriptor kernel are lane-private, but letting them of several
+    // batches overlap measured 1-2 % slower (they gather from per-batch candidate arrays and integral images, and together
+    // thrash L2), so the whole tail waits for the previous batch's.  Also ordered here: whatever the caller queued on the
+    // main stream before this call (bag-of-words reads of the rows, timers), and a pending row reset.
     if (c->batches > 0 && c->last_lane != li) CU(c, cudaStreamWaitEvent(st, P.advanced, 0));
-    // ... and whatever the caller queued on the main stream before this call (bag-of-words reads of the rows, timers)
     if (c->main_wait_pending) { CU(c, cudaStreamWaitEvent(st, c->main_mark, 0)); c->main_wait_pending = false; }
     if (c->reset_pending) { CU(c, cudaMemsetAsync(c->counters, 0, 4 * sizeof(uint32_t), st)); c->reset_pending = false; }
+    // second ordered compaction: kept keypoints -> row slots of this batch, per-pair row counts
     { Span s(c, P_COMPACT, 5, st);
       launch_keep_flags(st, g, L.cb);
       launch_exclusive_scan(st, L.cb.keep_scan, c->cand_cap, L.cb.live, L.scan_scratch);
-      launch_scatter_rows(st, g, L.cb, c->pair_rows);
+      launch_scatter_rows(st, g, L.cb, c->pair_rows + first);
     }
+    { Span s(c, P_COMPACT, 1, st);   launch_advance(st, g, L.cb); }
     if (!c->serial) CU(c, cudaStreamWaitEvent(st, L.aux_join, 0));
-    { Span s(c, P_DESCRIBE, 2, st);
+    { Span s(c, P_DESCRIBE, 1, st);
       launch_describe(st, g, c->store, c->store_frames, pl, L.maps.img, L.integral, L.cb, c->tb, c->rows_buf);
-      launch_advance(st, g, L.cb);
     }
     CU(c, cudaEventRecord(L.advanced, st));
     CU(c, cudaGetLastError());
@@ -477,8 +485,8 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
         CUC(dalloc(&L.cb.q_count, 4));
         CUC(dalloc(&L.cb.q0, L.cb.q_cap)); CUC(dalloc(&L.cb.q1, L.cb.q_cap)); CUC(dalloc(&L.cb.q2, L.cb.q_cap));
         CUC(dalloc(&L.cb.q1_up, (size_t)3 * L.cb.q_cap)); CUC(dalloc(&L.cb.q2_scan, (size_t)6 * L.cb.q_cap));
-        CUC(dalloc(&L.cb.live, 2));
-        CUC(cudaMemset(L.cb.live, 0, 2 * sizeof(uint32_t)));
+        CUC(dalloc(&L.cb.live, 4));
+        CUC(cudaMemset(L.cb.live, 0, 4 * sizeof(uint32_t)));
         L.cb.counters = c->counters;
         CUC(dalloc(&L.scan_scratch, scan_n / 2048 + 8));
         CUC(dalloc(&L.pairs, 3 * F));
@@ -917,6 +925,23 @@ int mfk_profile_read(mfk_ctx* c, mfk_prof_entry* entries, int cap, int* n_entrie
         n++;
     }
     *n_entries = n;
+    return MFK_OK;
+}
+
+int mfk_profile_timeline(mfk_ctx* c, mfk_span* spans, int cap, int* n_spans) {
+    if (!c || !spans || !n_spans || cap < 0) return MFK_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    { const int rc = sync_all(c); if (rc != MFK_OK) return rc; }
+    int n = 0;
+    for (const ProfSpan& s : c->spans) {
+        if (n >= cap) break;
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, c->t0, s.a) != cudaSuccess || cudaEventElapsedTime(&b, c->t0, s.b) != cudaSuccess) continue;
+        spans[n].name = kProfNames[s.id];
+        spans[n].start_ms = a; spans[n].end_ms = b;
+        n++;
+    }
+    *n_spans = n;
     return MFK_OK;
 }
 

@@ -40,7 +40,8 @@ struct CandBuf {                  // ordered candidate list of the batch + per-c
     uint32_t q_cap;
     uint32_t* counters;           // shared by all batches: [0] overflow flags (1 candidates, 2 rows), [1] rows accumulated
                                   // so far, [2] pairs accumulated so far, [3] live candidates of the last batch (copy)
-    uint32_t* live;               // [0] live candidate count of THIS batch (per buffer set), [1] its overflow flags until k_advance
+    uint32_t* live;               // [0] live candidate count of THIS batch (per buffer set), [1] its overflow flags until k_advance,
+                                  // [2] row ticket counter of k_describe, [3] rows_base of this batch (both set by k_advance)
 };
 
 enum { PEND_CAP = 2048 };         // per (pair, layer); beyond it phase B falls back to an ordered sweep
@@ -74,7 +75,7 @@ void launch_exclusive_scan(cudaStream_t, uint32_t* data, int n, const uint32_t* 
 void launch_phase_a(cudaStream_t, const Geom&, Maps, CandBuf, DeviceTables);
 void launch_phase_b(cudaStream_t, const Geom&, Maps, CandBuf, DeviceTables);
 void launch_keep_flags(cudaStream_t, const Geom&, CandBuf);           // flags -> keep_scan input
-void launch_scatter_rows(cudaStream_t, const Geom&, CandBuf, uint32_t* pair_rows);   // after the scan: row_src, per-pair counts
+void launch_scatter_rows(cudaStream_t, const Geom&, CandBuf, uint32_t* pair_rows);   // after the scan: row_src, per-pair counts (pair_rows = this batch's slice)
 void launch_advance(cudaStream_t, const Geom&, CandBuf);              // counters += this batch
 void launch_describe(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, const uint8_t* img,
                      const int32_t* integral, CandBuf, DeviceTables, void* rows /*mfk_row*/);

@@ -81,10 +81,17 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpScratch& ws = scratch[wib];
     const uint32_t n_rows = cb.keep_scan[cb.live[0]];
-    const uint32_t rows_base = cb.counters[1];
+    const uint32_t rows_base = cb.live[3];                         // saved by k_advance, which already ran for this batch
     const int W1 = g.W + 1;
     const size_t ipx = (size_t)W1 * (g.H + 1);
-    for (uint32_t r = blockIdx.x * DW + wib; r < n_rows; r += gridDim.x * DW) {
+    // rows differ a lot in cost (region staged or not, pattern scale), so warps draw row tickets instead of striding; the
+    // next ticket is drawn before the current row is processed, which hides the atomic's latency
+    uint32_t r = blockIdx.x * DW + wib;                            // first ticket is implicit
+    const uint32_t first_dynamic = gridDim.x * DW;
+    for (;;) {
+        if (r >= n_rows) break;
+        uint32_t next = 0;
+        if (lane == 0) next = first_dynamic + atomicAdd(&cb.live[2], 1u);
         if (rows_base + r >= (uint32_t)g.row_cap) break;            // overflow is flagged by k_advance
         const uint32_t c = cb.row_src[r];
         const int f = cb.meta[c] >> 3;
@@ -136,13 +143,23 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
             const uint4* src = reinterpret_cast<const uint4*>(&o);
             dst[0] = src[0]; dst[1] = src[1];
         }
-        __syncwarp();
+        __syncwarp();                                               // scratch is reused by the next row
+        r = __shfl_sync(0xffffffffu, next, 0);
     }
 }
 
 void launch_describe(cudaStream_t st, const Geom& g, const uint8_t* store, int store_frames, PairList pl, const uint8_t*,
                      const int32_t* integral, CandBuf cb, DeviceTables tb, void* rows) {
-    k_describe<<<148 * 6, DW * 32, 0, st>>>(g, store, store_frames, pl, integral, cb, tb, (RowOut*)rows);
+    // exactly one resident wave: tickets balance the rows, so a partial second wave would only add a tail
+    static int blocks = 0;
+    if (!blocks) {
+        int per_sm = 0, sms = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_describe, DW * 32, 0);
+        blocks = max(1, per_sm) * max(1, sms);
+    }
+    k_describe<<<blocks, DW * 32, 0, st>>>(g, store, store_frames, pl, integral, cb, tb, (RowOut*)rows);
 }
 
 // MIP bytes for caller-supplied keypoints on one frame pair (the MotionInterchangePatterns facade).

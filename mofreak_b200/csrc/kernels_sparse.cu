@@ -277,7 +277,7 @@ __global__ void k_scatter_rows(Geom g, CandBuf cb, uint32_t* __restrict__ pair_r
         if (cb.flags[i] & ST_KEEP) cb.row_src[cb.keep_scan[i]] = i;
     for (uint32_t i = tid; i < (uint32_t)g.F; i += nthreads) {
         const uint32_t b = min(cb.row_count[(size_t)i * g.rows], n), e = min(cb.row_count[(size_t)(i + 1) * g.rows], n);
-        pair_rows[cb.counters[2] + i] = cb.keep_scan[e] - cb.keep_scan[b];
+        pair_rows[i] = cb.keep_scan[e] - cb.keep_scan[b];
     }
 }
 
@@ -285,9 +285,12 @@ void launch_scatter_rows(cudaStream_t st, const Geom& g, CandBuf cb, uint32_t* p
     k_scatter_rows<<<148 * 8, 256, 0, st>>>(g, cb, pair_rows);
 }
 
+// the one serialised step between batches: this batch's base in the shared row accumulation, counters advanced
 __global__ void k_advance(Geom g, CandBuf cb) {
     const uint32_t rows = cb.keep_scan[cb.live[0]];
     const uint32_t have = cb.counters[1];
+    cb.live[3] = have;              // rows_base of this batch for k_describe
+    cb.live[2] = 0;                 // fresh row tickets for k_describe
     // overflow seen by this batch's lane-private kernels joins the shared flags here, behind any row reset
     if (cb.live[1]) { cb.counters[0] |= cb.live[1]; cb.live[1] = 0; }
     if (have + rows > (uint32_t)g.row_cap) { cb.counters[0] |= 2u; cb.counters[1] = (uint32_t)g.row_cap; }

@@ -258,3 +258,27 @@ def test_timer_and_profile_hooks():
         prof = ctx.profile_read()
         assert ms > 0 and ctx.launch_count() - before == 27
         assert prof["scores"][0] == 1 and prof["scores"][1] > 0 and prof["describe"][1] > 0
+
+
+@pytest.mark.gpu
+def test_profile_timeline_lists_every_launcher_call_in_stream_order():
+    clip = mofreak_b200.synth_clip(320, 240, 12, 5)
+    with mofreak_b200.Context(320, 240, 16, 2) as ctx:          # 7 pairs in batches of 2 -> 4 launch sequences on 4 lanes
+        ctx.upload_frames(clip)
+        ctx.profile_enable(True)
+        ctx.timer_start()
+        cur = np.arange(5, 12, dtype=np.int32)
+        ctx.extract_pairs(cur, cur - 5, cur - 1)
+        ms = ctx.timer_stop()
+        tl = ctx.profile_timeline()
+        names = [t[0] for t in tl]
+        assert names.count("scores") == 4 and names.count("describe") == 4 and names.count("compact") == 8
+        assert all(0.0 <= a <= b <= ms + 1e-3 for _, a, b in tl)
+        # within one launch sequence the families follow the dependency order
+        first = names[:names.index("describe") + 1]
+        assert first.index("absdiff") < first.index("scores") < first.index("phase_a") < first.index("phase_b") < first.index("describe")
+        prof = ctx.profile_read()
+        assert ctx.profile_timeline() == []                        # consumed by profile_read
+        assert prof["scores"][0] == 4
+        ctx.profile_enable(False)
+        ctx.fetch_rows(1 << 16)
