@@ -199,31 +199,33 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     __syncthreads();
     // ---- score, in two steps so that the 16-arc evaluation only runs where it can matter, on full warps:
     //   1. every pixel: ring loads + antipodal-pair bound (12 packed ops).  bound <= 0 proves S = 0 (most pixels of a
-    //      difference image: flat or noise).  The others are queued in shared memory.
-    //   2. the queue: full closed-form score (40 packed ops), score store, hit count.
-    // Per-thread invariants are hoisted; the kernel sits on the ALU pipe.
+    //      difference image: flat or noise).  Each thread remembers which of its 8 pixels are left; one block-wide scan
+    //      then queues them in shared memory.
+    //   2. the queue: full closed-form score (40 packed ops) into a shared score tile, hit mask.
+    // The score tile (zero where nothing was scored) leaves with 32-bit stores.  The kernel sits on the ALU/LSU pipes, so
+    // what counts is instructions per pixel.
     __shared__ uint16_t hard[SC_TW * SC_TH];
     __shared__ unsigned long long row_hits[SC_TH];      // bit x of word y: pixel (x0 + x, y0 + y) is a detector hit
-    __shared__ int n_hard;
-    if (tid == 0) n_hard = 0;
+    __shared__ __align__(16) uint8_t score_tile[SC_TH][SC_TW];
+    __shared__ int grp[65];                             // queue group sizes -> offsets; [64] = queue length
     if (tid < SC_TH) row_hits[tid] = 0ull;
+    reinterpret_cast<unsigned long long*>(&score_tile[0][0])[tid] = 0ull;          // 256 threads x 8 bytes = the tile
     const uint32_t* t0 = &tile[threadIdx.y + 3][threadIdx.x + 4];      // centre of this thread's first pixel
     const int xa = x0 + threadIdx.x, ya = y0 + threadIdx.y;
-    uint8_t* Sp = S_all + L.base + (size_t)f * L.px + (size_t)ya * w + xa;
-    bool in_x[SC_TW / 32], st_x[SC_TW / 32];
+    bool in_x[SC_TW / 32];
 #pragma unroll
     for (int jx = 0; jx < SC_TW / 32; jx++) {
         const int x = xa + 32 * jx;
         in_x[jx] = x >= 3 && x < w - 3;
-        st_x[jx] = x < w;
     }
-    __syncthreads();
+    uint32_t mine = 0;                                  // bit 2 * jy + jx: that pixel needs the full score
 #pragma unroll
     for (int jy = 0; jy < SC_TH / 8; jy++) {
         const int y = ya + 8 * jy;
-        const bool in_y = y >= 3 && y < h - 3, st_y = y < h;
+        const bool in_y = y >= 3 && y < h - 3;
 #pragma unroll
         for (int jx = 0; jx < SC_TW / 32; jx++) {
+            if (!(in_y && in_x[jx])) continue;
             const uint32_t* c = t0 + (8 * jy) * SC_SW + 32 * jx;
             // ring in circle order (oast9_16.h:214-232)
             uint32_t r[16];
@@ -231,22 +233,41 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
             r[4] = c[-3 * SC_SW];         r[5] = c[-3 * SC_SW + 1];     r[6] = c[-2 * SC_SW + 2];     r[7] = c[-SC_SW + 3];
             r[8] = c[3];                  r[9] = c[SC_SW + 3];          r[10] = c[2 * SC_SW + 2];     r[11] = c[3 * SC_SW + 1];
             r[12] = c[3 * SC_SW];         r[13] = c[3 * SC_SW - 1];     r[14] = c[2 * SC_SW - 2];     r[15] = c[SC_SW - 3];
-            const bool inside = in_y && in_x[jx];
-            const bool is_hard = inside && oast_score_bound_packed(r, c[0]) > 0;
-            if (!is_hard && st_y && st_x[jx]) Sp[(8 * jy) * w + 32 * jx] = 0;
-            const unsigned mask = __ballot_sync(0xffffffffu, is_hard);
-            if (mask) {
-                int base = 0;
-                if (threadIdx.x == 0) base = atomicAdd(&n_hard, __popc(mask));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (is_hard) hard[base + __popc(mask & ((1u << threadIdx.x) - 1u))] =
-                    (uint16_t)(((threadIdx.y + 8 * jy) << 6) | (threadIdx.x + 32 * jx));
-            }
+            if (oast_score_bound_packed(r, c[0]) > 0) mine |= 1u << (2 * jy + jx);
         }
     }
+    // Queue positions, in (pixel slot, warp, lane) order: entries that are neighbours in the queue are then neighbours in
+    // the tile row, so the ring loads of step 2 stay (nearly) free of bank conflicts.  8 ballots per warp give the group
+    // sizes; warp 0 scans the 64 groups.
+    const int lane = threadIdx.x, wrp = threadIdx.y;
+    uint32_t bal[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) bal[b] = __ballot_sync(0xffffffffu, (mine >> b) & 1u);
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < 8; b++) grp[8 * b + wrp] = __popc(bal[b]);
+    }
     __syncthreads();
-    const int nh = n_hard;
-    uint8_t* S = S_all + L.base + (size_t)f * L.px;
+    if (wrp == 0) {
+        const int a0 = grp[2 * lane], a1 = grp[2 * lane + 1];
+        int incl = a0 + a1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        const int excl = incl - a0 - a1;
+        grp[2 * lane] = excl; grp[2 * lane + 1] = excl + a0;
+        if (lane == 31) grp[64] = incl;
+    }
+    __syncthreads();
+    const int nh = grp[64];
+    const uint32_t below = (1u << lane) - 1u;
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+        if ((mine >> b) & 1u)
+            hard[grp[8 * b + wrp] + __popc(bal[b] & below)] = (uint16_t)(((threadIdx.y + 8 * (b >> 1)) << 6) | (threadIdx.x + 32 * (b & 1)));
+    __syncthreads();
     for (int i = tid; i < nh; i += 256) {
         const int ly = hard[i] >> 6, lx = hard[i] & 63;
         const uint32_t* c = &tile[ly + 3][lx + 4];
@@ -256,10 +277,26 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
         r[8] = c[3];                  r[9] = c[SC_SW + 3];          r[10] = c[2 * SC_SW + 2];     r[11] = c[3 * SC_SW + 1];
         r[12] = c[3 * SC_SW];         r[13] = c[3 * SC_SW - 1];     r[14] = c[2 * SC_SW - 2];     r[15] = c[SC_SW - 3];
         const int sc = oast_score_packed(r, c[0]);
-        S[(y0 + ly) * w + x0 + lx] = (uint8_t)sc;
+        score_tile[ly][lx] = (uint8_t)sc;
         if (sc >= BRISK_THRESHOLD) atomicOr(reinterpret_cast<unsigned*>(&row_hits[ly]) + (lx >> 5), 1u << (lx & 31));   // native 32-bit shared atomic
     }
     __syncthreads();
+    // the score tile, 8 bytes per thread
+    {
+        const int ry = tid >> 3, cx = (tid & 7) * 8;
+        const int y = y0 + ry;
+        if (y < h) {
+            uint8_t* dst = S_all + L.base + (size_t)f * L.px + (size_t)y * w + x0 + cx;
+            const bool words = (((uintptr_t)dst | (uintptr_t)w) & 3) == 0;     // odd frame sizes shift the layer bases
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&score_tile[ry][cx]);
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int x = x0 + cx + 4 * half;
+                if (words && x + 4 <= w) *reinterpret_cast<uint32_t*>(dst + 4 * half) = src[half];
+                else for (int j = 0; j < 4; j++) if (x + j < w) dst[4 * half + j] = score_tile[ry][cx + 4 * half + j];
+            }
+        }
+    }
     // one 64-bit word per (layer row, tile column); every word of the tile is written, so the map needs no clearing
     if (tid < SC_TH && y0 + tid < h)
         hitmask[((size_t)f * g.rows + L.row0 + y0 + tid) * mask_words + (t % tiles.across[l])] = row_hits[tid];
@@ -370,10 +407,12 @@ void launch_fill_candidates(cudaStream_t st, const Geom& g, const unsigned long 
 // integral image of the difference frame, int32 (H+1) x (W+1) with a zero top row / left column
 // ---------------------------------------------------------------------------------------------------
 // Two passes over the image, one write of the integral (the classic row-scan + column-scan writes and re-reads it):
-//   k_integral_left    per image row: left[y][s] = sum of the pixels left of 32-column strip s
-//   k_integral_strips  one warp per (pair, strip) walks down the rows keeping, per lane, the running column sum of the
-//                      in-strip row prefixes, and per warp the running sum of left[y][s]; their sum is the integral.
-constexpr int IG_STRIP = 32;
+//   k_integral_left    per image row: left[y][s] = sum of the pixels left of 128-column strip s
+//   k_integral_strips  one warp per (pair, strip) walks down the rows.  A lane owns 4 adjacent columns (one 32-bit read
+//                      per row): byte prefix inside the lane, one warp scan of the lane totals, four running column sums
+//                      in registers; the row's 128 results are transposed through shared memory so that every store
+//                      instruction writes 128 contiguous bytes.  0.3 instructions per pixel (2.1 with one column per lane).
+constexpr int IG_STRIP = 128;
 
 __global__ void k_integral_left(const uint8_t* __restrict__ img, int32_t* __restrict__ left, int W, int H, int F, int strips) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -382,67 +421,74 @@ __global__ void k_integral_left(const uint8_t* __restrict__ img, int32_t* __rest
     const uint8_t* row = img + (size_t)warp * W;                       // rows of all pairs are contiguous (layer 0 block)
     int32_t* out = left + (size_t)warp * strips;
     int carry = 0;
-    for (int s0 = 0; s0 < strips; s0 += 32) {
-        const int s = s0 + lane;
+    for (int s = 0; s < strips; s++) {                                 // the warp's 32 words of this iteration ARE strip s
+        const int x = s * IG_STRIP + 4 * lane;
         int sum = 0;
-        if (s < strips) {
-            const int x0 = s * IG_STRIP;
+        if (x + 4 <= W) sum = (int)__dp4a(load4(row + x), 0x01010101u, 0u);
+        else for (int j = 0; j < 4; j++) if (x + j < W) sum += row[x + j];
 #pragma unroll
-            for (int k = 0; k < IG_STRIP; k += 4) {
-                if (x0 + k + 4 <= W) sum = (int)__dp4a(load4(row + x0 + k), 0x01010101u, (unsigned)sum);
-                else for (int j = 0; j < 4; j++) if (x0 + k + j < W) sum += row[x0 + k + j];
-            }
-        }
-        int incl = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += n;
-        }
-        if (s < strips) out[s] = carry + incl - sum;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        if (lane == 0) out[s] = carry;
+        carry += sum;
     }
 }
 
 constexpr int IG_AHEAD = 8;       // rows fetched ahead of the dependent scan chain
+constexpr int IG_WARPS = 4;
 
-__global__ void k_integral_strips(const uint8_t* __restrict__ img, const int32_t* __restrict__ left, int32_t* __restrict__ integral,
-                                  int W, int H, int F, int strips) {
+__global__ void __launch_bounds__(IG_WARPS * 32)
+k_integral_strips(const uint8_t* __restrict__ img, const int32_t* __restrict__ left, int32_t* __restrict__ integral,
+                  int W, int H, int F, int strips) {
+    __shared__ __align__(16) int32_t xpose[IG_WARPS][IG_STRIP];
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (warp >= F * strips) return;
     const int f = warp / strips, s = warp - f * strips;
-    const int x = s * IG_STRIP + lane;
-    const bool live = x < W;
-    const uint8_t* col = img + (size_t)f * W * H + (live ? x : 0);
+    const int x = s * IG_STRIP + 4 * lane;                               // first of this lane's four columns
+    const int mine = min(max(W - x, 0), 4);                              // how many of them exist
+    const uint32_t keep = mine == 4 ? 0xffffffffu : ((1u << (8 * mine)) - 1u);
+    const uint8_t* col = img + (size_t)f * W * H + (mine ? x : 0);
     const int32_t* lf = left + (size_t)f * H * strips + s;
-    int32_t* out = integral + (size_t)f * (H + 1) * (W + 1);
-    if (live) out[x + 1] = 0;                                            // zero top row
-    if (s == 0 && lane == 0) out[0] = 0;
-    int col_acc = 0, left_acc = 0;
+    int32_t* out = integral + (size_t)f * (H + 1) * (W + 1) + 1 + s * IG_STRIP;      // column s * 128 of the image = integral column + 1
+    bool st[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) st[k] = s * IG_STRIP + 32 * k + lane < W;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (st[k]) out[32 * k + lane] = 0;                  // zero top row
+    if (s == 0 && lane == 0) out[-1] = 0;
+    int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, left_acc = 0;
+    int32_t* xp = xpose[wib];
     for (int y0 = 0; y0 < H; y0 += IG_AHEAD) {
-        int px[IG_AHEAD], lv[IG_AHEAD];
+        uint32_t px[IG_AHEAD];
+        int lv[IG_AHEAD];
 #pragma unroll
         for (int k = 0; k < IG_AHEAD; k++) {
             const int y = y0 + k;
-            px[k] = (live && y < H) ? col[(size_t)y * W] : 0;
+            px[k] = (mine && y < H) ? (load4(col + (size_t)y * W) & keep) : 0u;
             lv[k] = (y < H) ? lf[(size_t)y * strips] : 0;
         }
 #pragma unroll
         for (int k = 0; k < IG_AHEAD; k++) {
             const int y = y0 + k;
             if (y >= H) break;
-            int incl = px[k];
+            const uint32_t v = px[k];
+            const int p0 = (int)(v & 0xffu), p1 = p0 + (int)((v >> 8) & 0xffu), p2 = p1 + (int)((v >> 16) & 0xffu), p3 = p2 + (int)(v >> 24);
+            int incl = p3;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const int n = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += n;
             }
-            col_acc += incl;
             left_acc += lv[k];
+            const int before = incl - p3;                                  // row sum left of this lane inside the strip
+            acc0 += before + p0; acc1 += before + p1; acc2 += before + p2; acc3 += before + p3;
+            *reinterpret_cast<int4*>(&xp[4 * lane]) = make_int4(acc0 + left_acc, acc1 + left_acc, acc2 + left_acc, acc3 + left_acc);
+            __syncwarp();
             int32_t* o = out + (size_t)(y + 1) * (W + 1);
-            if (live) o[x + 1] = col_acc + left_acc;
-            if (s == 0 && lane == 0) o[0] = 0;                           // zero left column
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (st[q]) o[32 * q + lane] = xp[32 * q + lane];
+            if (s == 0 && lane == 0) o[-1] = 0;                            // zero left column
+            __syncwarp();
         }
     }
 }
@@ -452,7 +498,7 @@ void launch_integral(cudaStream_t st, const Geom& g, const uint8_t* img, int32_t
     const int warps1 = g.F * g.H;
     k_integral_left<<<(warps1 * 32 + 255) / 256, 256, 0, st>>>(img, left, g.W, g.H, g.F, strips);
     const int warps2 = g.F * strips;
-    k_integral_strips<<<(warps2 * 32 + 127) / 128, 128, 0, st>>>(img, left, integral, g.W, g.H, g.F, strips);
+    k_integral_strips<<<(warps2 + IG_WARPS - 1) / IG_WARPS, IG_WARPS * 32, 0, st>>>(img, left, integral, g.W, g.H, g.F, strips);
 }
 
 // ---------------------------------------------------------------------------------------------------
