@@ -342,65 +342,45 @@ void launch_row_counts(cudaStream_t st, const Geom& g, const unsigned long long*
 }
 
 // ---------------------------------------------------------------------------------------------------
-// ordered candidate list: one warp per FILL_ROWS (pair, layer) rows; a row's hits are written at its scanned offset in
-// x order, read from the hit masks (one 64-bit word per lane)
+// ordered candidate list: one THREAD per (pair, layer) row walks the row's hit-mask words and writes the hits in x order at
+// the row's scanned offset.  (One warp per row with a shuffle scan of the word counts cost 40x the instructions: a row has
+// ~8 hits in <= 12 words, far too little for 32 lanes.)
 // ---------------------------------------------------------------------------------------------------
-constexpr int FILL_ROWS = 8;      // consecutive (pair, layer) rows per warp
-
 __global__ void k_fill_candidates(Geom g, const unsigned long long* __restrict__ hitmask, int mask_words, CandBuf cb) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const int rowi = blockIdx.x * blockDim.x + threadIdx.x;
     const int total_rows = g.F * g.rows;
-    if (warp == 0 && lane == 0 && cb.row_count[total_rows] > (uint32_t)g.cand_cap) atomicOr(&cb.live[1], 1u);
-    const int row_begin = warp * FILL_ROWS;
-    if (row_begin >= total_rows) return;
-    const int row_end = min(row_begin + FILL_ROWS, total_rows);
-    // the 9 offsets of this warp's rows, one per lane
-    const uint32_t my_off = cb.row_count[min(row_begin + lane, total_rows)];
-    if (__shfl_sync(0xffffffffu, my_off, 0) == __shfl_sync(0xffffffffu, my_off, row_end - row_begin)) return;   // no hits at all
-    for (int rowi = row_begin; rowi < row_end; rowi++) {
-        const uint32_t begin = __shfl_sync(0xffffffffu, my_off, rowi - row_begin);
-        const uint32_t end = __shfl_sync(0xffffffffu, my_off, rowi - row_begin + 1);
-        if (begin == end) continue;
-        const int f = rowi / g.rows, rr = rowi - f * g.rows;
-        int l = 0;
+    if (rowi == 0 && cb.row_count[total_rows] > (uint32_t)g.cand_cap) atomicOr(&cb.live[1], 1u);
+    if (rowi >= total_rows) return;
+    uint32_t at = cb.row_count[rowi];
+    const uint32_t end = cb.row_count[rowi + 1];
+    if (at == end) return;
+    const int f = rowi / g.rows, rr = rowi - f * g.rows;
+    int l = 0;
 #pragma unroll
-        for (int k = 1; k < N_LAYERS; k++) l += (rr >= g.L[k].row0);
-        const LayerGeom& L = g.L[l];
-        const int y = rr - L.row0;
-        const int words = (L.w + SC_TW - 1) / SC_TW;
-        const unsigned long long* m = hitmask + (size_t)rowi * mask_words;
-        uint32_t pos = begin;
-        for (int w0 = 0; w0 < words; w0 += 32) {
-            unsigned long long bits = (w0 + lane < words) ? m[w0 + lane] : 0ull;
-            const int cnt = __popcll(bits);
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int nb = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += nb;
+    for (int k = 1; k < N_LAYERS; k++) l += (rr >= g.L[k].row0);
+    const uint32_t y16 = (uint32_t)(rr - g.L[l].row0) << 16;
+    const uint32_t meta = ((uint32_t)f << 3) | (uint32_t)l;
+    const int words = (g.L[l].w + SC_TW - 1) / SC_TW;
+    const unsigned long long* m = hitmask + (size_t)rowi * mask_words;
+    const uint32_t cap = (uint32_t)g.cand_cap;
+    for (int k = 0; k < words && at < end; k++) {
+        unsigned long long bits = m[k];
+        while (bits) {
+            const int b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (at < cap) {
+                cb.xy[at] = (uint32_t)(k * SC_TW + b) | y16;
+                cb.meta[at] = meta;
+                cb.flags[at] = 0;
             }
-            uint32_t at = pos + (uint32_t)(incl - cnt);
-            const int xbase = (w0 + lane) * SC_TW;
-            while (bits) {
-                const int b = __ffsll((long long)bits) - 1;
-                bits &= bits - 1;
-                if (at < (uint32_t)g.cand_cap) {
-                    cb.xy[at] = (uint32_t)(xbase + b) | ((uint32_t)y << 16);
-                    cb.meta[at] = ((uint32_t)f << 3) | (uint32_t)l;
-                    cb.flags[at] = 0;
-                }
-                at++;
-            }
-            pos += (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
+            at++;
         }
     }
 }
 
 void launch_fill_candidates(cudaStream_t st, const Geom& g, const unsigned long long* hitmask, CandBuf cb) {
-    const int warps = (g.F * g.rows + FILL_ROWS - 1) / FILL_ROWS;
-    const int blocks = (warps * 32 + 255) / 256;
-    k_fill_candidates<<<blocks, 256, 0, st>>>(g, hitmask, score_mask_words(g.W), cb);
+    const int rows = g.F * g.rows;
+    k_fill_candidates<<<(rows + 127) / 128, 128, 0, st>>>(g, hitmask, score_mask_words(g.W), cb);
 }
 
 // ---------------------------------------------------------------------------------------------------
