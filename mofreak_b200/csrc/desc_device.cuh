@@ -154,6 +154,33 @@ __device__ __forceinline__ int resize_px(const uint8_t* __restrict__ roi, int st
     return min(max(v, 0), 255);
 }
 
+// The taps of one destination row / column with everything that does not depend on the other axis folded in once per
+// keypoint (clamps, the row offset in bytes, the column shift of a region staged from an aligned address): the per-pixel
+// work is then four byte reads and the fixed-point blend.  Same arithmetic as resize_px.
+struct RowTap { int32_t o0, o1, b0, b1; };
+struct ColTap { int32_t x0, x1, a0, a1; };
+
+__device__ __forceinline__ RowTap row_tap(const ResizeTap t, int s, int stride) {
+    RowTap r;
+    r.o0 = min(max((int)t.ofs, 0), s - 1) * stride;
+    r.o1 = min(max((int)t.ofs + 1, 0), s - 1) * stride;
+    r.b0 = t.by0; r.b1 = t.by1;
+    return r;
+}
+__device__ __forceinline__ ColTap col_tap(const ResizeTap t, int s, int shift) {
+    ColTap c;
+    c.x0 = t.xofs + shift;
+    c.x1 = min((int)t.xofs + 1, s - 1) + shift;
+    c.a0 = t.ax0; c.a1 = t.ax1;
+    return c;
+}
+__device__ __forceinline__ int resize_px_flat(const uint8_t* __restrict__ roi, const RowTap ty, const ColTap tx) {
+    const int R0 = roi[ty.o0 + tx.x0] * tx.a0 + roi[ty.o0 + tx.x1] * tx.a1;
+    const int R1 = roi[ty.o1 + tx.x0] * tx.a0 + roi[ty.o1 + tx.x1] * tx.a1;
+    const int v = (((ty.b0 * (R0 >> 4)) >> 16) + ((ty.b1 * (R1 >> 4)) >> 16) + 2) >> 2;
+    return min(max(v, 0), 255);
+}
+
 // the same destination pixel of two regions that share their geometry (frame t and t-5): taps, clamps and offsets once
 __device__ __forceinline__ void resize_px_pair(const uint8_t* __restrict__ roi_a, const uint8_t* __restrict__ roi_b, int stride, int s,
                                                const ResizeTap ty, const ResizeTap tx, int& va, int& vb) {
@@ -171,12 +198,11 @@ __device__ __forceinline__ void resize_px_pair(const uint8_t* __restrict__ roi_a
 // the row-major buffer starting at the patch's top-left corner: the reference walks ROI .data linearly
 // (MoFREAKUtilities.cpp:79-88), and that is part of the output contract.  Centres :307-316, shifts :55-70.
 __device__ __forceinline__ int mip_ssd(const uint8_t* cur19, const uint8_t* prev19, int c, int k) {
-    const int CX[8] = {5, 5, 5, 9, 9, 13, 13, 13};
-    const int CY[8] = {5, 9, 13, 5, 13, 5, 9, 13};
-    const int SX[8] = {-4, -3, 0, 3, 4, 3, 0, -3};
-    const int SY[8] = {0, 3, 4, 3, 0, -3, -4, -3};
-    const uint8_t* p = cur19 + (CY[c] - 1) * PATCH + (CX[c] - 1);
-    const uint8_t* q = prev19 + (CY[c] + SY[k] - 1) * PATCH + (CX[c] + SX[k] - 1);
+    // centre and shift tables as nibbles of one word each (indexable without a stack array): CX, CY, SX + 4, SY + 4
+    const int cx = (int)((0xDDD99555u >> (4 * c)) & 15u), cy = (int)((0xD95D5D95u >> (4 * c)) & 15u);
+    const int sx = (int)((0x14787410u >> (4 * k)) & 15u) - 4, sy = (int)((0x10147874u >> (4 * k)) & 15u) - 4;
+    const uint8_t* p = cur19 + (cy - 1) * PATCH + (cx - 1);
+    const uint8_t* q = prev19 + (cy + sy - 1) * PATCH + (cx + sx - 1);
     int ssd = 0;
 #pragma unroll
     for (int i = 0; i < 9; i++) { const int d = (int)p[i] - (int)q[i]; ssd += d * d; }

@@ -20,42 +20,68 @@ constexpr int DW = 8;                 // warps per block
 constexpr int PATCH_PAD = 368;        // 19 x 19 = 361 patch bytes, padded
 
 constexpr int ROI_MAX = 32;           // regions of interest up to this side are staged in shared memory
+constexpr int ROI_WORDS = 9;          // aligned 32-bit words that cover 32 columns from any byte offset
+constexpr int ROI_STRIDE = 4 * ROI_WORDS + 4;    // bytes per staged row (40: keeps rows 8-byte aligned)
 
 struct WarpScratch {
-    alignas(4) uint8_t roi[2][ROI_MAX * ROI_MAX];
+    alignas(16) uint8_t roi[2][ROI_MAX * ROI_STRIDE];
+    alignas(16) RowTap rtap[PATCH];   // per destination row / column of the 19 x 19 patch
+    alignas(16) ColTap ctap[PATCH];
     uint8_t cur[PATCH_PAD], prev[PATCH_PAD];
     uint8_t field[2][44];             // receptive-field means: unrotated, rotated
-    ResizeTap tap[PATCH];             // per destination index; the same table serves rows and columns
 };
 
+// Region of interest (side s <= ROI_MAX at tl_x, tl_y) of both gray frames -> shared memory, as the aligned words that
+// cover it: staged column = image column - (tl_x & ~3).  With a frame width that is a multiple of 4 the words are aligned
+// in global memory too and travel with cp.async, so the copy runs under the FREAK arithmetic of the same row; wait with
+// roi_ready().  Other widths take the synchronous path (unaligned reads assembled by load4).
+__device__ __forceinline__ void roi_stage(WarpScratch& ws, const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
+                                          int W, int tl_x, int tl_y, int s, int lane, bool async) {
+    const int ax = tl_x & ~3;
+    const int nw = ((tl_x & 3) + s + 3) >> 2;                       // words per row, <= 9
+    const size_t org = (size_t)tl_y * W + ax;
+    for (int i = lane; i < s * ROI_WORDS; i += 32) {
+        const int r = i / ROI_WORDS, k = i - r * ROI_WORDS;
+        if (k >= nw) continue;
+        const size_t off = org + (size_t)r * W + 4 * k;
+        uint8_t* d0 = &ws.roi[0][r * ROI_STRIDE + 4 * k];
+        uint8_t* d1 = &ws.roi[1][r * ROI_STRIDE + 4 * k];
+        if (async) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(d0)), "l"(cur + off));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(d1)), "l"(prev + off));
+        } else {
+            *reinterpret_cast<uint32_t*>(d0) = load4(cur + off);
+            *reinterpret_cast<uint32_t*>(d1) = load4(prev + off);
+        }
+    }
+    if (async) asm volatile("cp.async.commit_group;");
+}
+
+__device__ __forceinline__ void roi_ready(bool async) {
+    if (async) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+}
+
 // cv::resize(ROI s x s -> 19 x 19, INTER_LINEAR) for both frames into scratch (fixed-point bilinear of OpenCV's
-// imgwarp.cpp: 11-bit coefficients, vertical pass ((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2 >> 2)
+// imgwarp.cpp: 11-bit coefficients, vertical pass ((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2 >> 2).  Regions up to
+// ROI_MAX must have been staged (roi_stage + roi_ready); larger ones are read from global memory.
 __device__ __forceinline__ void resize_roi_pair(WarpScratch& ws, const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
                                                 int W, int tl_x, int tl_y, int s, int lane, const DeviceTables& tb) {
-    if (lane < PATCH) ws.tap[lane] = resize_tap(s, lane);
-    __syncwarp();
-    const uint8_t* c0 = cur + (size_t)tl_y * W + tl_x;
-    const uint8_t* p0 = prev + (size_t)tl_y * W + tl_x;
     const bool staged = s <= ROI_MAX;
-    if (staged) {
-        // stage both regions with 32-bit reads (8 lanes per row, 4 rows per step), then interpolate from shared memory
-        for (int i = lane; i < s * 8; i += 32) {
-            const int r = i >> 3, c4 = (i & 7) * 4;
-            if (c4 < s) {
-                *reinterpret_cast<uint32_t*>(&ws.roi[0][r * ROI_MAX + c4]) = load4(c0 + r * W + c4);
-                *reinterpret_cast<uint32_t*>(&ws.roi[1][r * ROI_MAX + c4]) = load4(p0 + r * W + c4);
-            }
-        }
-        __syncwarp();
+    if (lane < PATCH) {
+        const ResizeTap t = resize_tap(s, lane);
+        ws.rtap[lane] = row_tap(t, s, staged ? ROI_STRIDE : W);
+        ws.ctap[lane] = col_tap(t, s, staged ? (tl_x & 3) : 0);
     }
+    __syncwarp();
+    const uint8_t* src0 = staged ? ws.roi[0] : cur + (size_t)tl_y * W + tl_x;
+    const uint8_t* src1 = staged ? ws.roi[1] : prev + (size_t)tl_y * W + tl_x;
     // only the 276 of the 2 x 361 patch pixels that the SSD tests read are interpolated
     for (int i = lane; i < tb.n_mip_needed; i += 32) {
         const int e = tb.mip_needed[i];
-        const int fr = e >> 15, p = e & 0x7fff;
-        const int dy = p / PATCH, dx = p - dy * PATCH;
-        const int v = staged ? resize_px(ws.roi[fr], ROI_MAX, s, ws.tap[dy], ws.tap[dx])
-                             : resize_px(fr ? p0 : c0, W, s, ws.tap[dy], ws.tap[dx]);
-        (fr ? ws.prev : ws.cur)[p] = (uint8_t)v;
+        const int fr = e >> 15, dx = e & 31, dy = (e >> 5) & 31;
+        const int v = resize_px_flat(fr ? src1 : src0, ws.rtap[dy], ws.ctap[dx]);
+        (fr ? ws.prev : ws.cur)[dy * PATCH + dx] = (uint8_t)v;
     }
     __syncwarp();
 }
@@ -99,6 +125,15 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
         const int sidx = cb.scale_idx[c];
         const int32_t* I = integral + (size_t)f * ipx;
 
+        // --- MIP geometry first: the two regions of interest start travelling to shared memory now and are needed last ---
+        const uint8_t* cur = store + (size_t)(pl.cur_slot[f] % store_frames) * g.L[0].px;
+        const uint8_t* prev = store + (size_t)(pl.prev_slot[f] % store_frames) * g.L[0].px;
+        const int xi = (int)kx, yi = (int)ky;                          // float -> int at the call, :460
+        const int half = (int)ksize / 2;
+        const int side = (int)ceilf(ksize);
+        const bool async = (g.W & 3) == 0;
+        if (side <= ROI_MAX) roi_stage(ws, cur, prev, g.W, xi - half, yi - half, side, lane, async);
+
         // --- FREAK: orientation from the unrotated pattern ---
         const FreakPoint* P0 = tb.points + (size_t)sidx * FREAK_ORIENTATIONS * FREAK_POINTS;
         for (int p = lane; p < FREAK_POINTS; p += 32) ws.field[0][p] = (uint8_t)mean_intensity(I, W1, P0[p], kx, ky);
@@ -126,22 +161,15 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
         }
 
         // --- MIP on the gray frames ---
-        const uint8_t* cur = store + (size_t)(pl.cur_slot[f] % store_frames) * g.L[0].px;
-        const uint8_t* prev = store + (size_t)(pl.prev_slot[f] % store_frames) * g.L[0].px;
-        const int xi = (int)kx, yi = (int)ky;                          // float -> int at the call, :460
-        const int half = (int)ksize / 2;
-        const int side = (int)ceilf(ksize);
+        if (side <= ROI_MAX) roi_ready(async);
         resize_roi_pair(ws, cur, prev, g.W, xi - half, yi - half, side, lane, tb);
         uint32_t mot[2];
         mip_bits(ws, lane, mot);
 
-        if (lane == 0) {
-            RowOut o;
-            o.x = kx; o.y = ky; o.frame = pl.label[f]; o.scale = ksize;
-            o.app[0] = app[0]; o.app[1] = app[1]; o.mot[0] = mot[0]; o.mot[1] = mot[1];
+        if (lane == 0) {                                            // one row = two 16-byte stores, built in registers
             uint4* dst = reinterpret_cast<uint4*>(rows + rows_base + r);
-            const uint4* src = reinterpret_cast<const uint4*>(&o);
-            dst[0] = src[0]; dst[1] = src[1];
+            dst[0] = make_uint4(__float_as_uint(kx), __float_as_uint(ky), (uint32_t)pl.label[f], __float_as_uint(ksize));
+            dst[1] = make_uint4(app[0], app[1], mot[0], mot[1]);
         }
         __syncwarp();                                               // scratch is reused by the next row
         r = __shfl_sync(0xffffffffu, next, 0);
@@ -178,6 +206,7 @@ k_mip_only(int W, int H, const uint8_t* __restrict__ cur, const uint8_t* __restr
             if (lane == 0) { atomicOr(err, 1u); for (int i = 0; i < 8; i++) motion[8 * r + i] = 0; }
             continue;
         }
+        if (side <= ROI_MAX) { roi_stage(ws, cur, prev, W, tl_x, tl_y, side, lane, false); roi_ready(false); }
         resize_roi_pair(ws, cur, prev, W, tl_x, tl_y, side, lane, tb);
         uint32_t mot[2];
         mip_bits(ws, lane, mot);

@@ -129,7 +129,7 @@ void fill_mip_needed(Tables& T) {
     int n = 0;
     for (int fr = 0; fr < 2; fr++)
         for (int p = 0; p < 361; p++)
-            if (need[fr][p]) T.mip_needed[n++] = (uint16_t)(p | (fr << 15));
+            if (need[fr][p]) T.mip_needed[n++] = (uint16_t)((p % 19) | ((p / 19) << 5) | (fr << 15));     // dx | dy << 5 | frame << 15
     T.n_mip_needed = n;
 }
 

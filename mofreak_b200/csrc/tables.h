@@ -26,7 +26,7 @@ struct Tables {
     OrientPair  orient[FREAK_ORIENT_PAIRS];
     UsedPair    used[FREAK_USED_PAIRS];
     // MIP: the pixels of the two 19x19 patches that the 64 SSD tests actually read (51 of the current-frame patch, 225 of
-    // the previous-frame patch); entry = pixel index | 0x8000 for the previous frame.  Only these are interpolated.
+    // the previous-frame patch); entry = dx | dy << 5 | 0x8000 for the previous frame.  Only these are interpolated.
     uint16_t    mip_needed[2 * 361];
     int32_t     n_mip_needed;
 };

@@ -224,15 +224,19 @@ int hh_extract_pair(const uint8_t* cur, const uint8_t* prev, int w, int h, int l
         for (int i = 0; i < 64; i++) if (field[H.tb.used[i].i] >= field[H.tb.used[i].j]) app[i >> 3] |= (uint8_t)(1u << (i & 7));
         const int xi = (int)kx, yi = (int)ky, half = (int)ksize / 2, side = (int)ceilf(ksize);
         uint8_t a19[PATCH * PATCH], b19[PATCH * PATCH];
-        ResizeTap tap[PATCH];
-        for (int d = 0; d < PATCH; d++) tap[d] = resize_tap(side, d);
+        RowTap rtap[PATCH]; ColTap ctap[PATCH];
+        for (int d = 0; d < PATCH; d++) {
+            const ResizeTap t = resize_tap(side, d);
+            rtap[d] = row_tap(t, side, w); ctap[d] = col_tap(t, side, 0);
+        }
         const uint8_t* c0 = cur + (size_t)(yi - half) * w + (xi - half);
         const uint8_t* p0 = prev + (size_t)(yi - half) * w + (xi - half);
         memset(a19, 0xEE, sizeof a19); memset(b19, 0xEE, sizeof b19);      // pixels the SSD tests never read stay unset
         for (int i = 0; i < H.tb.n_mip_needed; i++) {
-            const int e = H.tb.mip_needed[i], fr = e >> 15, p = e & 0x7fff;
-            const int v = resize_px(fr ? p0 : c0, w, side, tap[p / PATCH], tap[p % PATCH]);
-            (fr ? b19 : a19)[p] = (uint8_t)v;
+            const int e = H.tb.mip_needed[i], fr = e >> 15, dx = e & 31, dy = (e >> 5) & 31;
+            const int v = resize_px_flat(fr ? p0 : c0, rtap[dy], ctap[dx]);
+            if (v != resize_px(fr ? p0 : c0, w, side, resize_tap(side, dy), resize_tap(side, dx))) abort();   // flat == reference form
+            (fr ? b19 : a19)[dy * PATCH + dx] = (uint8_t)v;
         }
         for (int i = 0; i < 64; i++) if (mip_ssd(a19, b19, i >> 3, i & 7) > 288) mot[i >> 3] |= (uint8_t)(1u << (i & 7));
         if (n < cap) {
