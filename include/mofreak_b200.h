@@ -71,6 +71,12 @@ int  mfk_sync(mfk_ctx* ctx);                      /* waits for the context's str
  * slots slot0 .. slot0+n_frames-1 (indices taken modulo store_frames).  Async when `gray` is pinned.
  * Replaces: frame_queue.push(frame.clone()) of MoFREAKUtilities.cpp:391-399, 485-487. */
 int  mfk_upload_frames(mfk_ctx* ctx, const uint8_t* gray, size_t stride, int n_frames, int slot0);
+/* Frame ingest from interleaved 8-bit BGR: uploads n_frames frames (stride = bytes per source row,
+ * >= 3 * width) and converts them to gray ON THE DEVICE into slots slot0.. exactly as cv::cvtColor(CV_BGR2GRAY)
+ * does for the reference (MoFREAKUtilities.cpp:395, 410): (B*cb + G*cg + R*cr + half) >> bits.  coeff_bits = 14
+ * selects OpenCV 2.4's coefficients 1868/9617/4899 (the reference's version; recalled, not verifiable offline),
+ * 15 those of OpenCV >= 3 (3735/19235/9798; verified against cv2 4.13).  Async, like mfk_upload_frames. */
+int  mfk_upload_frames_bgr(mfk_ctx* ctx, const uint8_t* bgr, size_t stride, int n_frames, int slot0, int coeff_bits);
 /* Device address of slot 0 and the store capacity, for producers that already live on the GPU
  * (decoder output, synthetic generators).  Slots are dense: slot k starts at base + k*width*height. */
 int  mfk_frame_store(mfk_ctx* ctx, uint8_t** device_base, int* store_frames);

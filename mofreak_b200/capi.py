@@ -21,7 +21,7 @@ assert ROW_DTYPE.itemsize == 32
 
 # every symbol include/mofreak_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "mfk_create", "mfk_create_ex", "mfk_destroy", "mfk_last_error", "mfk_sync", "mfk_upload_frames", "mfk_frame_store",
+    "mfk_create", "mfk_create_ex", "mfk_destroy", "mfk_last_error", "mfk_sync", "mfk_upload_frames", "mfk_upload_frames_bgr", "mfk_frame_store",
     "mfk_extract_pairs", "mfk_fetch_rows", "mfk_rows_device", "mfk_reset_rows", "mfk_extract_clip", "mfk_rows_text", "mfk_format_rows", "mfk_extract_clip_text", "mfk_mip_describe",
     "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram",
     "mfk_allreduce_counts", "mfk_nccl_unique_id", "mfk_nccl_comm_init", "mfk_nccl_comm_destroy", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read", "mfk_profile_timeline",
@@ -62,6 +62,7 @@ def lib():
     L.mfk_last_error.argtypes = [p]; L.mfk_last_error.restype = C.c_char_p
     L.mfk_sync.argtypes = [p]
     L.mfk_upload_frames.argtypes = [p, u8p, C.c_size_t, C.c_int, C.c_int]
+    L.mfk_upload_frames_bgr.argtypes = [p, u8p, C.c_size_t, C.c_int, C.c_int, C.c_int]
     L.mfk_frame_store.argtypes = [p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     L.mfk_extract_pairs.argtypes = [p, i32p, i32p, i32p, C.c_int]
     L.mfk_fetch_rows.argtypes = [p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), u32p, C.c_size_t]
@@ -152,6 +153,12 @@ class Context:
         frames = np.ascontiguousarray(frames, np.uint8)
         assert frames.ndim == 3 and frames.shape[1:] == (self.height, self.width)
         self._check(self._L.mfk_upload_frames(self._h, _ptr(frames), self.width, frames.shape[0], slot0))
+
+    def upload_frames_bgr(self, frames_bgr, slot0=0, coeff_bits=14):
+        """frames_bgr: uint8 [n, H, W, 3]; converted to gray on the device (cv::cvtColor(BGR2GRAY) arithmetic)."""
+        f = np.ascontiguousarray(frames_bgr, np.uint8)
+        assert f.ndim == 4 and f.shape[1:] == (self.height, self.width, 3)
+        self._check(self._L.mfk_upload_frames_bgr(self._h, _ptr(f), self.width * 3, f.shape[0], slot0, coeff_bits))
 
     def upload_raw(self, host_ptr, n_frames, slot0=0):
         """host_ptr: integer address of (ideally pinned) dense frames."""

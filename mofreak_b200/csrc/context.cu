@@ -101,6 +101,8 @@ struct mfk_ctx {
     size_t text_buf_cap = 0;
     mfk_row* text_rows = nullptr;
     size_t text_rows_cap = 0;
+    uint8_t* bgr_stage = nullptr;         // BGR frames on their way into the gray store (mfk_upload_frames_bgr)
+    size_t bgr_stage_bytes = 0;
     // last batch (debug access)
     Geom last{};
     bool have_last = false;
@@ -328,7 +330,7 @@ void destroy(mfk_ctx* c) {
     cudaFree(c->rows_buf); cudaFree(c->pair_rows);
     for (void* p : c->tb_alloc) cudaFree(p);
     cudaFree(c->codebook); cudaFree(c->bow_counts); cudaFree(c->bow_tmp);
-    cudaFree(c->text_off); cudaFree(c->text_buf); cudaFree(c->text_rows);
+    cudaFree(c->text_off); cudaFree(c->text_buf); cudaFree(c->text_rows); cudaFree(c->bgr_stage);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->upload_done) cudaEventDestroy(c->upload_done);
@@ -532,6 +534,42 @@ int mfk_upload_frames(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_fram
     }
     CU(c, cudaEventRecord(c->upload_done, c->copy_stream));
     c->upload_pending = true;
+    return MFK_OK;
+}
+
+int mfk_upload_frames_bgr(mfk_ctx* c, const uint8_t* bgr, size_t stride, int n_frames, int slot0, int coeff_bits) {
+    if (!c || !bgr || n_frames < 0 || slot0 < 0 || (coeff_bits != 14 && coeff_bits != 15))
+        return fail(c, MFK_ERR_ARG, "bad argument to mfk_upload_frames_bgr (coeff_bits is 14 or 15)");
+    if (stride < (size_t)c->W * 3) return fail(c, MFK_ERR_ARG, "stride %zu < 3 * width %d", stride, c->W);
+    if (n_frames > c->store_frames) return fail(c, MFK_ERR_ARG, "%d frames do not fit a store of %d", n_frames, c->store_frames);
+    CU(c, cudaSetDevice(c->device));
+    const size_t px = (size_t)c->W * c->H;
+    const int chunk = 32;                             // frames per staging round
+    if (c->bgr_stage_bytes < (size_t)chunk * px * 3) {
+        CU(c, cudaStreamSynchronize(c->copy_stream));
+        cudaFree(c->bgr_stage); c->bgr_stage = nullptr; c->bgr_stage_bytes = 0;
+        CU(c, cudaMalloc((void**)&c->bgr_stage, (size_t)chunk * px * 3 + 16));
+        c->bgr_stage_bytes = (size_t)chunk * px * 3;
+    }
+    int done = 0;
+    while (done < n_frames) {
+        const int slot = (slot0 + done) % c->store_frames;
+        const int run = std::min(std::min(n_frames - done, c->store_frames - slot), chunk);
+        for (auto& r : c->readers)
+            if (r.valid && r.lo <= slot + run - 1 && r.hi >= slot)
+                for (int k = 0; k < mfk_ctx::MAX_LANES; k++) if (r.on[k]) CU(c, cudaStreamWaitEvent(c->copy_stream, r.ev[k], 0));
+        const uint8_t* src = bgr + (size_t)done * stride * c->H;
+        // the staging buffer is reused in stream order: the previous round's conversion kernel runs before this copy
+        CU(c, cudaMemcpy2DAsync(c->bgr_stage, (size_t)c->W * 3, src, stride, (size_t)c->W * 3, (size_t)run * c->H,
+                                cudaMemcpyHostToDevice, c->copy_stream));
+        uint8_t* dst = c->store + (size_t)slot * px;
+        launch_bgr2gray(c->copy_stream, c->bgr_stage, dst, (size_t)run * px, coeff_bits);
+        c->launches++;
+        done += run;
+    }
+    CU(c, cudaEventRecord(c->upload_done, c->copy_stream));
+    c->upload_pending = true;
+    CU(c, cudaGetLastError());
     return MFK_OK;
 }
 

@@ -57,6 +57,8 @@ struct DeviceTables {             // device copies of mfk::Tables
 };
 
 // --- dense stage ------------------------------------------------------------------------------------
+// interleaved BGR -> gray as cv::cvtColor computes it (coeff_bits 14: OpenCV 2.4, 15: OpenCV >= 3)
+void launch_bgr2gray(cudaStream_t, const uint8_t* bgr, uint8_t* gray, size_t n_px, int coeff_bits);
 // pair descriptions travel as kernel parameters (no staging copy, no host stall): 256 per launch; returns launches made
 int launch_set_pairs(cudaStream_t, const int32_t* cur_host, const int32_t* prev_host, const int32_t* label_host, int n, PairList dst);
 void launch_absdiff(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, uint8_t* img);

@@ -43,6 +43,51 @@ __global__ void k_absdiff(const uint8_t* __restrict__ store, int store_frames, c
 }
 
 // ---------------------------------------------------------------------------------------------------
+// frame ingest: interleaved BGR -> gray, cv::cvtColor(CV_BGR2GRAY) on 8-bit data
+// (call sites MoFREAKUtilities.cpp:395, 410).  OpenCV's fixed-point form: (B*cb + G*cg + R*cr + half) >> bits with
+// 14-bit coefficients 1868 / 9617 / 4899 in OpenCV 2.4 (the reference's version) and 15-bit 3735 / 19235 / 9798 from 3.x on.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_bgr2gray(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, size_t n_px, int cb, int cg, int cr, int bits) {
+    const size_t quad = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // 4 pixels = 12 source bytes = 3 aligned words
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int half = 1 << (bits - 1);
+    for (size_t q = quad; q * 4 < n_px; q += stride) {
+        if (q * 4 + 4 <= n_px) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(bgr) + q * 3;
+            const uint32_t w0 = src[0], w1 = src[1], w2 = src[2];            // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+            const int y0 = ((int)(w0 & 0xff) * cb + (int)((w0 >> 8) & 0xff) * cg + (int)((w0 >> 16) & 0xff) * cr + half) >> bits;
+            const int y1 = ((int)(w0 >> 24) * cb + (int)(w1 & 0xff) * cg + (int)((w1 >> 8) & 0xff) * cr + half) >> bits;
+            const int y2 = ((int)((w1 >> 16) & 0xff) * cb + (int)(w1 >> 24) * cg + (int)(w2 & 0xff) * cr + half) >> bits;
+            const int y3 = ((int)((w2 >> 8) & 0xff) * cb + (int)((w2 >> 16) & 0xff) * cg + (int)(w2 >> 24) * cr + half) >> bits;
+            reinterpret_cast<uint32_t*>(gray)[q] = (uint32_t)y0 | ((uint32_t)y1 << 8) | ((uint32_t)y2 << 16) | ((uint32_t)y3 << 24);
+        } else {
+            for (size_t p = q * 4; p < n_px; p++)
+                gray[p] = (uint8_t)(((int)bgr[3 * p] * cb + (int)bgr[3 * p + 1] * cg + (int)bgr[3 * p + 2] * cr + half) >> bits);
+        }
+    }
+}
+
+__global__ void k_bgr2gray_bytes(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, size_t n_px, int cb, int cg, int cr, int bits) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int half = 1 << (bits - 1);
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += stride)
+        gray[p] = (uint8_t)(((int)bgr[3 * p] * cb + (int)bgr[3 * p + 1] * cg + (int)bgr[3 * p + 2] * cr + half) >> bits);
+}
+
+// word path when both pointers are 4-byte aligned (always, for frame sizes that are a multiple of 4 pixels), else bytes
+void launch_bgr2gray(cudaStream_t st, const uint8_t* bgr, uint8_t* gray, size_t n_px, int coeff_bits) {
+    if (n_px == 0) return;
+    const bool v24 = coeff_bits == 14;
+    const int cb = v24 ? 1868 : 3735, cg = v24 ? 9617 : 19235, cr = v24 ? 4899 : 9798, bits = v24 ? 14 : 15;
+    if ((((uintptr_t)bgr | (uintptr_t)gray) & 3) == 0) {
+        const size_t quads = (n_px + 3) / 4;
+        k_bgr2gray<<<(unsigned)min((quads + 255) / 256, (size_t)148 * 16), 256, 0, st>>>(bgr, gray, n_px, cb, cg, cr, bits);
+    } else {
+        k_bgr2gray_bytes<<<(unsigned)min((n_px + 255) / 256, (size_t)148 * 16), 256, 0, st>>>(bgr, gray, n_px, cb, cg, cr, bits);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // pair descriptions: the host arrays ride in the kernel parameter block, 256 pairs (3 KB) per launch
 // ---------------------------------------------------------------------------------------------------
 struct PairChunk { int32_t cur[256], prev[256], label[256]; };

@@ -1,7 +1,11 @@
 #!/usr/bin/env python
-"""Frame ingest outside the hot path: decode a video and convert BGR -> gray exactly as the reference does
+"""Frame ingest outside the hot path: decode a video and convert BGR -> gray as the reference does
 (cv::VideoCapture + cv::cvtColor(CV_BGR2GRAY), MoFREAKUtilities.cpp:380-410), writing the raw MFKGRAY1 container that
 MoFREAKUtilities::computeMoFREAKFromFile of mofreak_b200/host reads.
+
+The gray conversion is OpenCV 2.4's (the reference's version): (B*1868 + G*9617 + R*4899 + 8192) >> 14.  OpenCV >= 3
+uses 15-bit coefficients and differs in about 0.3 % of the pixels; pass --cv3 for that arithmetic.  The same two forms
+are available on the device (mfk_upload_frames_bgr, coeff_bits 14 / 15).
 
     python mofreak_b200/tools/video_to_y8.py in.avi out.y8
 """
@@ -26,9 +30,17 @@ def read_y8(path):
         return np.frombuffer(f.read(), np.uint8).reshape(n, h, w)
 
 
+def bgr_to_gray(bgr, cv3=False):
+    cb, cg, cr, bits = (3735, 19235, 9798, 15) if cv3 else (1868, 9617, 4899, 14)
+    b, g, r = (bgr[..., i].astype(np.int64) for i in range(3))
+    return ((b * cb + g * cg + r * cr + (1 << (bits - 1))) >> bits).astype(np.uint8)
+
+
 def main():
     import cv2
-    src, dst = sys.argv[1], sys.argv[2]
+    args = [a for a in sys.argv[1:] if a != "--cv3"]
+    cv3 = "--cv3" in sys.argv
+    src, dst = args[0], args[1]
     cap = cv2.VideoCapture(src)
     if not cap.isOpened():
         raise SystemExit("Could not open file: " + src)
@@ -37,7 +49,7 @@ def main():
         ok, frame = cap.read()
         if not ok:
             break
-        frames.append(cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY))
+        frames.append(bgr_to_gray(frame, cv3))
     write_y8(dst, np.stack(frames))
     print("%s: %d frames %dx%d" % (dst, len(frames), frames[0].shape[1], frames[0].shape[0]))
 

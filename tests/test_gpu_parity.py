@@ -282,3 +282,33 @@ def test_profile_timeline_lists_every_launcher_call_in_stream_order():
         assert prof["scores"][0] == 4
         ctx.profile_enable(False)
         ctx.fetch_rows(1 << 16)
+
+
+def _gray_fixed_point(bgr, bits):
+    cb, cg, cr = (1868, 9617, 4899) if bits == 14 else (3735, 19235, 9798)
+    b, g, r = (bgr[..., i].astype(np.int64) for i in range(3))
+    return ((b * cb + g * cg + r * cr + (1 << (bits - 1))) >> bits).astype(np.uint8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(160, 120), (53, 49)])
+@pytest.mark.parametrize("bits", [14, 15])
+def test_bgr_ingest_matches_cvtcolor_arithmetic(shape, bits):
+    w, h = shape
+    rng = np.random.default_rng(21)
+    n = 5
+    bgr = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    want = _gray_fixed_point(bgr, bits)
+    if bits == 15:
+        cv2 = pytest.importorskip("cv2")                     # OpenCV >= 3 arithmetic is what this container's cv2 computes
+        assert np.array_equal(want[0], cv2.cvtColor(bgr[0], cv2.COLOR_BGR2GRAY))
+    with mofreak_b200.Context(w, h, 2 * n, n) as ctx:
+        ctx.upload_frames_bgr(bgr, slot0=0, coeff_bits=bits)      # device conversion into slots 0..n-1
+        ctx.upload_frames(want, slot0=n)                           # host conversion into slots n..2n-1
+        cur = np.arange(n, dtype=np.int32)
+        ctx.extract_pairs(cur, cur + n, cur)
+        for pair in range(n):                                       # layer 0 is |slot cur - slot prev|: zero iff identical
+            assert not ctx.debug_layer(0, 0, pair).any()
+        ctx.fetch_rows(1 << 16)
+        with pytest.raises(mofreak_b200.MofreakError):
+            ctx.upload_frames_bgr(bgr, coeff_bits=16)
