@@ -4,6 +4,7 @@
 #include <string>
 
 #include "BagOfWordsRepresentation.h"
+#include "Clustering.h"
 #include "MoFREAKUtilities.h"
 #include "MotionInterchangePatterns.h"
 
@@ -77,6 +78,29 @@ int mfkh_mip(const uint8_t* cur, const uint8_t* prev, int w, int h, float scale,
     mip.extractMotionByMotionInterchangePatterns(d, scale, x, y);
     for (int i = 0; i < 8; i++) out8[i] = (uint8_t)d[i];
     return 0;
+}
+
+// Clustering over .mofreak files grouped by class (the shape of cluster(), main.cpp:160-213): for each class its files are
+// read (at most 50000 / n_files features per file), randomClusters(true) takes num_clust / num_classes of them, and
+// clusters.txt is written once at the end.  seed 0 = time(NULL) as in the reference.
+int mfkh_cluster(int num_clust, int num_classes, const char* svm_path, const char** files, const int* file_class, int n_files, unsigned seed) {
+    std::vector<int> classes;
+    for (int c = 1; c <= num_classes; c++) classes.push_back(c);
+    Clustering clustering(16, num_clust, 0, num_classes, classes, svm_path);
+    clustering.setAppearanceDescriptor(8, true);
+    clustering.setMotionDescriptor(8, true);
+    clustering.setSeed(seed);
+    for (int c = 1; c <= num_classes; c++) {
+        MoFREAKUtilities u(MoFREAKUtilities::KTH);
+        int count = 0;
+        for (int i = 0; i < n_files; i++) count += file_class[i] == c;
+        if (!count) continue;
+        for (int i = 0; i < n_files; i++) if (file_class[i] == c) u.readMoFREAKFeatures(files[i], 50000 / count);
+        clustering.buildDataFromMoFREAK(u.getMoFREAKFeatures(), false, false);
+        clustering.randomClusters(true);
+    }
+    clustering.writeClusters(false);
+    return clustering.centersFilled();
 }
 
 }  // extern "C"

@@ -67,6 +67,36 @@ def test_gray_video_container(host, tmp_path):
     assert raw[20:] == clip.tobytes()
 
 
+def _cluster(host, tmp_path, files, classes, K, n_classes, seed):
+    arr = (C.c_char_p * len(files))(*[str(f).encode() for f in files])
+    cls = (C.c_int * len(files))(*classes)
+    host.mfkh_cluster.argtypes = [C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.c_int, C.c_uint]
+    filled = host.mfkh_cluster(K, n_classes, str(tmp_path).encode(), arr, cls, len(files), seed)
+    text = (tmp_path / "clusters.txt").read_text()
+    cb = np.array([[int(t) for t in line.split()] for line in text.split("\n") if line], np.uint8)
+    return filled, text, cb
+
+
+def test_codebook_selection_is_seeded_balanced_and_drawn_from_the_class(host, tmp_path):
+    """Clustering::randomClusters (Clustering.cpp:165-213) with an explicit seed: reproducible, an equal quota per class,
+    every codeword one of that class's descriptors, clusters.txt in the format loadClusters reads."""
+    names = ["kth_160x120x100_seed1", "ucf_320x240x12_seed3", "trecvid_720x576x7_seed5"]
+    files = []
+    for i, n in enumerate(names):
+        f = tmp_path / ("class%d.mofreak" % (i + 1)); f.write_text(util.golden_text(n)); files.append(f)
+    K, n_classes = 12, 3
+    filled, text, cb = _cluster(host, tmp_path, files, [1, 2, 3], K, n_classes, 7)
+    assert filled == K and cb.shape == (K, 16)
+    assert text == clusters_text(cb)                                   # K lines of 16 integers, each followed by a space
+    for c, n in enumerate(names):
+        rows = util.golden_rows(n)
+        pool = {bytes(r["appearance"]) + bytes(r["motion"]) for r in rows}
+        for k in range(4 * c, 4 * c + 4):                               # K / classes consecutive codewords per class
+            assert bytes(cb[k]) in pool
+    assert _cluster(host, tmp_path, files, [1, 2, 3], K, n_classes, 7)[1] == text        # same seed, same file
+    assert _cluster(host, tmp_path, files, [1, 2, 3], K, n_classes, 8)[1] != text        # another seed, another draw
+
+
 # ---------------------------------------------------------------------------------------------- GPU side
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["kth_160x120x100_seed1", "odd_212x163x9_seed7"])
