@@ -411,6 +411,7 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     if (width < 48 || height < 48 || width > 8192 || height > 8192)
         return fail(nullptr, MFK_ERR_ARG, "frame size %dx%d outside 48..8192", width, height);
     if (store_frames < MFK_FRAME_GAP + 1 || max_pairs < 1) return fail(nullptr, MFK_ERR_ARG, "store_frames >= 6 and max_pairs >= 1 required");
+    if (max_pairs > 65535) return fail(nullptr, MFK_ERR_ARG, "max_pairs <= 65535 (pairs index a grid dimension); longer requests are split into launch sequences anyway");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

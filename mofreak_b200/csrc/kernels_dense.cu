@@ -210,19 +210,22 @@ constexpr int SC_TW = 64, SC_TH = 32;                 // output tile
 constexpr int SC_SW = SC_TW + 8, SC_SH = SC_TH + 6;   // staged: columns x0-4 .. x0+67, rows y0-3 .. y0+34
 constexpr int SC_WORDS = SC_SW / 4;                   // aligned words per staged row
 
-struct ScoreTiles { int first[N_LAYERS + 1]; int across[N_LAYERS]; };   // tile index ranges per layer
+struct ScoreTiles { int first_row[N_LAYERS + 1]; int across[N_LAYERS]; };   // tile-row ranges and tile columns per layer
 
 __global__ void __launch_bounds__(256)
 k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tiles, const uint8_t* __restrict__ img_all,
          uint8_t* __restrict__ S_all, unsigned long long* __restrict__ hitmask, int mask_words) {
     __shared__ __align__(16) uint32_t tile[SC_SH][SC_SW];
-    const int f = blockIdx.y;
+    // grid = (widest layer's tile columns, tile rows of all layers, pairs): no division to find the tile; the blocks
+    // beyond a narrower layer's last column leave at once
+    const int f = blockIdx.z;
     int l = 0;
 #pragma unroll
-    for (int k = 1; k < N_LAYERS; k++) l += ((int)blockIdx.x >= tiles.first[k]);
+    for (int k = 1; k < N_LAYERS; k++) l += ((int)blockIdx.y >= tiles.first_row[k]);
+    const int tcol = blockIdx.x;
+    if (tcol >= tiles.across[l]) return;
     const LayerGeom& L = g.L[l];
-    const int t = blockIdx.x - tiles.first[l];
-    const int x0 = (t % tiles.across[l]) * SC_TW, y0 = (t / tiles.across[l]) * SC_TH;
+    const int x0 = tcol * SC_TW, y0 = ((int)blockIdx.y - tiles.first_row[l]) * SC_TH;
     const int w = L.w, h = L.h;
     const uint8_t* img = img_all + L.base + (size_t)f * L.px;
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -344,21 +347,23 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     }
     // one 64-bit word per (layer row, tile column); every word of the tile is written, so the map needs no clearing
     if (tid < SC_TH && y0 + tid < h)
-        hitmask[((size_t)f * g.rows + L.row0 + y0 + tid) * mask_words + (t % tiles.across[l])] = row_hits[tid];
+        hitmask[((size_t)f * g.rows + L.row0 + y0 + tid) * mask_words + tcol] = row_hits[tid];
 }
 
 int score_mask_words(int frame_width) { return (frame_width + SC_TW - 1) / SC_TW; }
 
 void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* S, unsigned long long* hitmask) {
     ScoreTiles tiles;
-    int total = 0;
+    int rows = 0, widest = 0;
     for (int l = 0; l < N_LAYERS; l++) {
-        tiles.first[l] = total;
+        tiles.first_row[l] = rows;
         tiles.across[l] = (g.L[l].w + SC_TW - 1) / SC_TW;
-        total += tiles.across[l] * ((g.L[l].h + SC_TH - 1) / SC_TH);
+        widest = max(widest, tiles.across[l]);
+        rows += (g.L[l].h + SC_TH - 1) / SC_TH;
     }
-    tiles.first[N_LAYERS] = total;
-    k_scores<<<dim3(total, g.F), dim3(32, 8), 0, st>>>(g, tiles, img, S, hitmask, score_mask_words(g.W));
+    tiles.first_row[N_LAYERS] = rows;
+    // gridDim.z <= 65535 pairs per launch sequence (context.cu caps max_pairs far below)
+    k_scores<<<dim3(widest, rows, g.F), dim3(32, 8), 0, st>>>(g, tiles, img, S, hitmask, score_mask_words(g.W));
 }
 
 // ---------------------------------------------------------------------------------------------------
