@@ -466,6 +466,33 @@ __global__ void k_integral_left(const uint8_t* __restrict__ img, int32_t* __rest
 constexpr int IG_AHEAD = 8;       // rows fetched ahead of the dependent scan chain
 constexpr int IG_WARPS = 4;
 
+// one image row of one strip: the lane's four pixels v (packed), the sum of the row left of the strip -> running column sums,
+// transposed through shared memory so that each store instruction covers 128 contiguous bytes
+__device__ __forceinline__ void integral_row(uint32_t v, int left_of_strip, int lane, int& acc0, int& acc1, int& acc2, int& acc3,
+                                             int& left_acc, int32_t* xp, int32_t* o, const bool st0, const bool st1, const bool st2,
+                                             const bool st3, const bool first_strip) {
+    const int p0 = (int)(v & 0xffu), p1 = p0 + (int)((v >> 8) & 0xffu), p2 = p1 + (int)((v >> 16) & 0xffu), p3 = p2 + (int)(v >> 24);
+    int incl = p3;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    left_acc += left_of_strip;
+    const int before = incl - p3;                                  // row sum left of this lane inside the strip
+    acc0 += before + p0; acc1 += before + p1; acc2 += before + p2; acc3 += before + p3;
+    *reinterpret_cast<int4*>(&xp[4 * lane]) = make_int4(acc0 + left_acc, acc1 + left_acc, acc2 + left_acc, acc3 + left_acc);
+    __syncwarp();
+    if (st0) o[lane] = xp[lane];
+    if (st1) o[32 + lane] = xp[32 + lane];
+    if (st2) o[64 + lane] = xp[64 + lane];
+    if (st3) o[96 + lane] = xp[96 + lane];
+    if (first_strip && lane == 0) o[-1] = 0;                       // zero left column
+    __syncwarp();
+}
+
+// ALIGNED: frame width and layer base are multiples of 4, so a lane's four pixels are one aligned word
+template <bool ALIGNED>
 __global__ void __launch_bounds__(IG_WARPS * 32)
 k_integral_strips(const uint8_t* __restrict__ img, const int32_t* __restrict__ left, int32_t* __restrict__ integral,
                   int W, int H, int F, int strips) {
@@ -477,49 +504,41 @@ k_integral_strips(const uint8_t* __restrict__ img, const int32_t* __restrict__ l
     const int x = s * IG_STRIP + 4 * lane;                               // first of this lane's four columns
     const int mine = min(max(W - x, 0), 4);                              // how many of them exist
     const uint32_t keep = mine == 4 ? 0xffffffffu : ((1u << (8 * mine)) - 1u);
-    const uint8_t* col = img + (size_t)f * W * H + (mine ? x : 0);
+    const uint8_t* col = img + (size_t)f * W * H + (mine ? x : 0);       // walks down one row per step
     const int32_t* lf = left + (size_t)f * H * strips + s;
-    int32_t* out = integral + (size_t)f * (H + 1) * (W + 1) + 1 + s * IG_STRIP;      // column s * 128 of the image = integral column + 1
-    bool st[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) st[k] = s * IG_STRIP + 32 * k + lane < W;
-#pragma unroll
-    for (int k = 0; k < 4; k++) if (st[k]) out[32 * k + lane] = 0;                  // zero top row
-    if (s == 0 && lane == 0) out[-1] = 0;
+    int32_t* o = integral + (size_t)f * (H + 1) * (W + 1) + 1 + s * IG_STRIP;        // column s * 128 of the image = integral column + 1
+    const bool st0 = s * IG_STRIP + lane < W, st1 = s * IG_STRIP + 32 + lane < W, st2 = s * IG_STRIP + 64 + lane < W,
+               st3 = s * IG_STRIP + 96 + lane < W;
+    const bool first_strip = s == 0;
+    if (st0) o[lane] = 0;                                                // zero top row
+    if (st1) o[32 + lane] = 0;
+    if (st2) o[64 + lane] = 0;
+    if (st3) o[96 + lane] = 0;
+    if (first_strip && lane == 0) o[-1] = 0;
     int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, left_acc = 0;
     int32_t* xp = xpose[wib];
-    for (int y0 = 0; y0 < H; y0 += IG_AHEAD) {
+    const int W1 = W + 1;
+    int y = 0;
+    for (; y + IG_AHEAD <= H; y += IG_AHEAD) {                           // whole groups: loads first, then the dependent chain
         uint32_t px[IG_AHEAD];
         int lv[IG_AHEAD];
 #pragma unroll
         for (int k = 0; k < IG_AHEAD; k++) {
-            const int y = y0 + k;
-            px[k] = (mine && y < H) ? (load4(col + (size_t)y * W) & keep) : 0u;
-            lv[k] = (y < H) ? lf[(size_t)y * strips] : 0;
+            px[k] = ALIGNED ? *reinterpret_cast<const uint32_t*>(col) : load4(col);
+            lv[k] = *lf;
+            col += W; lf += strips;
         }
 #pragma unroll
         for (int k = 0; k < IG_AHEAD; k++) {
-            const int y = y0 + k;
-            if (y >= H) break;
-            const uint32_t v = px[k];
-            const int p0 = (int)(v & 0xffu), p1 = p0 + (int)((v >> 8) & 0xffu), p2 = p1 + (int)((v >> 16) & 0xffu), p3 = p2 + (int)(v >> 24);
-            int incl = p3;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += n;
-            }
-            left_acc += lv[k];
-            const int before = incl - p3;                                  // row sum left of this lane inside the strip
-            acc0 += before + p0; acc1 += before + p1; acc2 += before + p2; acc3 += before + p3;
-            *reinterpret_cast<int4*>(&xp[4 * lane]) = make_int4(acc0 + left_acc, acc1 + left_acc, acc2 + left_acc, acc3 + left_acc);
-            __syncwarp();
-            int32_t* o = out + (size_t)(y + 1) * (W + 1);
-#pragma unroll
-            for (int q = 0; q < 4; q++) if (st[q]) o[32 * q + lane] = xp[32 * q + lane];
-            if (s == 0 && lane == 0) o[-1] = 0;                            // zero left column
-            __syncwarp();
+            o += W1;
+            integral_row(px[k] & keep, lv[k], lane, acc0, acc1, acc2, acc3, left_acc, xp, o, st0, st1, st2, st3, first_strip);
         }
+    }
+    for (; y < H; y++) {                                                 // the last H % 8 rows
+        const uint32_t v = ALIGNED ? *reinterpret_cast<const uint32_t*>(col) : load4(col);
+        const int l = *lf;
+        col += W; lf += strips; o += W1;
+        integral_row(v & keep, l, lane, acc0, acc1, acc2, acc3, left_acc, xp, o, st0, st1, st2, st3, first_strip);
     }
 }
 
@@ -528,7 +547,9 @@ void launch_integral(cudaStream_t st, const Geom& g, const uint8_t* img, int32_t
     const int warps1 = g.F * g.H;
     k_integral_left<<<(warps1 * 32 + 255) / 256, 256, 0, st>>>(img, left, g.W, g.H, g.F, strips);
     const int warps2 = g.F * strips;
-    k_integral_strips<<<(warps2 + IG_WARPS - 1) / IG_WARPS, IG_WARPS * 32, 0, st>>>(img, left, integral, g.W, g.H, g.F, strips);
+    const int blocks = (warps2 + IG_WARPS - 1) / IG_WARPS;
+    if ((((uintptr_t)img | (uintptr_t)g.W) & 3) == 0) k_integral_strips<true><<<blocks, IG_WARPS * 32, 0, st>>>(img, left, integral, g.W, g.H, g.F, strips);
+    else k_integral_strips<false><<<blocks, IG_WARPS * 32, 0, st>>>(img, left, integral, g.W, g.H, g.F, strips);
 }
 
 // ---------------------------------------------------------------------------------------------------
