@@ -312,3 +312,32 @@ def test_bgr_ingest_matches_cvtcolor_arithmetic(shape, bits):
         ctx.fetch_rows(1 << 16)
         with pytest.raises(mofreak_b200.MofreakError):
             ctx.upload_frames_bgr(bgr, coeff_bits=16)
+
+
+@pytest.mark.gpu
+def test_back_to_back_steps_and_interleaved_contexts_agree(orc):
+    """The bench's shapes: steps queued back to back without a sync (the row reset is applied in-line, the front of step
+    k + 1 runs under the tail of step k), and two contexts alternating (the end-to-end double buffer)."""
+    clip = mofreak_b200.synth_clip(320, 240, 21, 31)
+    want = orc.extract_clip(clip)
+    cur = np.arange(5, 21, dtype=np.int32)
+    with mofreak_b200.Context(320, 240, 21, 3) as a, mofreak_b200.Context(320, 240, 21, 5) as b:
+        a.upload_frames(clip); b.upload_frames(clip)
+        for _ in range(4):                                   # only the last step's rows may remain
+            a.reset_rows()
+            a.extract_pairs(cur, cur - 5, cur - 1)
+        rows, per = a.fetch_rows(len(want) + 8, len(cur))
+        assert util.rows_equal(rows, want) and per.sum() == len(want)
+        got = []
+        for k in range(4):                                   # submit on one context, then fetch the other one's previous step
+            c = (a, b)[k % 2]
+            c.reset_rows()
+            c.extract_pairs(cur, cur - 5, cur - 1)
+            if k:
+                got.append((a, b)[(k - 1) % 2].fetch_rows(len(want) + 8)[0])
+        got.append(b.fetch_rows(len(want) + 8)[0])
+        assert all(util.rows_equal(g, want) for g in got) and len(got) == 4
+        # a reset that no launch sequence consumed is applied by the next reader
+        a.extract_pairs(cur[:2], cur[:2] - 5, cur[:2] - 1)
+        a.reset_rows()
+        assert a.rows_device()[1] == 0 and a.rows_text() == b""
