@@ -255,7 +255,6 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     __shared__ uint16_t hard[SC_TW * SC_TH];
     __shared__ unsigned long long row_hits[SC_TH];      // bit x of word y: pixel (x0 + x, y0 + y) is a detector hit
     __shared__ __align__(16) uint8_t score_tile[SC_TH][SC_TW];
-    __shared__ int grp[65];                             // queue group sizes -> offsets; [64] = queue length
     if (tid < SC_TH) row_hits[tid] = 0ull;
     reinterpret_cast<unsigned long long*>(&score_tile[0][0])[tid] = 0ull;          // 256 threads x 8 bytes = the tile
     const uint32_t* t0 = &tile[threadIdx.y + 3][threadIdx.x + 4];      // centre of this thread's first pixel
@@ -284,40 +283,23 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
             if (oast_score_bound_packed(r, c[0]) > 0) mine |= 1u << (2 * jy + jx);
         }
     }
-    // Queue positions, in (pixel slot, warp, lane) order: entries that are neighbours in the queue are then neighbours in
-    // the tile row, so the ring loads of step 2 stay (nearly) free of bank conflicts.  8 ballots per warp give the group
-    // sizes; warp 0 scans the 64 groups.
+    // Each warp queues its own survivors (8 ballots, no block-wide scan or barrier) in (pixel slot, lane) order, so queue
+    // neighbours are tile-row neighbours and the ring loads of step 2 stay (nearly) free of bank conflicts; it then scores
+    // them 32 at a time.
     const int lane = threadIdx.x, wrp = threadIdx.y;
-    uint32_t bal[8];
-#pragma unroll
-    for (int b = 0; b < 8; b++) bal[b] = __ballot_sync(0xffffffffu, (mine >> b) & 1u);
-    if (lane == 0) {
-#pragma unroll
-        for (int b = 0; b < 8; b++) grp[8 * b + wrp] = __popc(bal[b]);
-    }
-    __syncthreads();
-    if (wrp == 0) {
-        const int a0 = grp[2 * lane], a1 = grp[2 * lane + 1];
-        int incl = a0 + a1;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += n;
-        }
-        const int excl = incl - a0 - a1;
-        grp[2 * lane] = excl; grp[2 * lane + 1] = excl + a0;
-        if (lane == 31) grp[64] = incl;
-    }
-    __syncthreads();
-    const int nh = grp[64];
+    uint16_t* queue = hard + wrp * (SC_TW * SC_TH / 8);
     const uint32_t below = (1u << lane) - 1u;
+    int nh = 0;
 #pragma unroll
-    for (int b = 0; b < 8; b++)
+    for (int b = 0; b < 8; b++) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (mine >> b) & 1u);
         if ((mine >> b) & 1u)
-            hard[grp[8 * b + wrp] + __popc(bal[b] & below)] = (uint16_t)(((threadIdx.y + 8 * (b >> 1)) << 6) | (threadIdx.x + 32 * (b & 1)));
-    __syncthreads();
-    for (int i = tid; i < nh; i += 256) {
-        const int ly = hard[i] >> 6, lx = hard[i] & 63;
+            queue[nh + __popc(bal & below)] = (uint16_t)(((threadIdx.y + 8 * (b >> 1)) << 6) | (threadIdx.x + 32 * (b & 1)));
+        nh += __popc(bal);
+    }
+    __syncwarp();
+    for (int i = lane; i < nh; i += 32) {
+        const int ly = queue[i] >> 6, lx = queue[i] & 63;
         const uint32_t* c = &tile[ly + 3][lx + 4];
         uint32_t r[16];
         r[0] = c[-3];                 r[1] = c[-SC_SW - 3];         r[2] = c[-2 * SC_SW - 2];     r[3] = c[-3 * SC_SW - 1];
