@@ -74,14 +74,24 @@ __device__ __forceinline__ void resize_roi_pair(WarpScratch& ws, const uint8_t* 
         ws.ctap[lane] = col_tap(t, s, staged ? (tl_x & 3) : 0);
     }
     __syncwarp();
-    const uint8_t* src0 = staged ? ws.roi[0] : cur + (size_t)tl_y * W + tl_x;
-    const uint8_t* src1 = staged ? ws.roi[1] : prev + (size_t)tl_y * W + tl_x;
-    // only the 276 of the 2 x 361 patch pixels that the SSD tests read are interpolated
-    for (int i = lane; i < tb.n_mip_needed; i += 32) {
-        const int e = tb.mip_needed[i];
-        const int fr = e >> 15, dx = e & 31, dy = (e >> 5) & 31;
-        const int v = resize_px_flat(fr ? src1 : src0, ws.rtap[dy], ws.ctap[dx]);
-        (fr ? ws.prev : ws.cur)[dy * PATCH + dx] = (uint8_t)v;
+    // only the 276 of the 2 x 361 patch pixels that the SSD tests read are interpolated.  Two copies of the loop so that
+    // the staged one reads through shared-memory loads (a pointer that may be either space costs generic loads)
+    if (staged) {
+        for (int i = lane; i < tb.n_mip_needed; i += 32) {
+            const int e = tb.mip_needed[i];
+            const int fr = e >> 15, dx = e & 31, dy = (e >> 5) & 31;
+            const int v = resize_px_flat(ws.roi[fr], ws.rtap[dy], ws.ctap[dx]);
+            (fr ? ws.prev : ws.cur)[dy * PATCH + dx] = (uint8_t)v;
+        }
+    } else {
+        const uint8_t* src0 = cur + (size_t)tl_y * W + tl_x;
+        const uint8_t* src1 = prev + (size_t)tl_y * W + tl_x;
+        for (int i = lane; i < tb.n_mip_needed; i += 32) {
+            const int e = tb.mip_needed[i];
+            const int fr = e >> 15, dx = e & 31, dy = (e >> 5) & 31;
+            const int v = resize_px_flat(fr ? src1 : src0, ws.rtap[dy], ws.ctap[dx]);
+            (fr ? ws.prev : ws.cur)[dy * PATCH + dx] = (uint8_t)v;
+        }
     }
     __syncwarp();
 }
