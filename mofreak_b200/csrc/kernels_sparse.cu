@@ -76,17 +76,30 @@ __global__ void __launch_bounds__(PA_THREADS) k_pa_above(const __grid_constant__
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool pass = false;
         uint32_t c = 0;
+        int li = 0;
         Scan up = neutral_scan();
         if (i < n) {
             c = cb.q0[i];
             const uint32_t xy = cb.xy[c], meta = cb.meta[c];
             PairView pv; pv.g = &g; pv.m = m; pv.f = meta >> 3;
-            pass = stage_above(pv, cb, meta & 7, xy & 0xffff, xy >> 16, c, up);
+            li = meta & 7;
+            pass = stage_above(pv, cb, li, xy & 0xffff, xy >> 16, c, up);
         }
-        const uint32_t slot = warp_append(&cb.q_count[1], pass);
-        if (pass) {
+        // layer-0 candidates have no layer below (the AGAST-5/8 stand-in is part of the emit step): they go straight to the
+        // emit queue, so that k_pa_below runs on full warps of candidates that really scan
+        const bool to_emit = pass && li == 0, to_below = pass && li != 0;
+        const uint32_t slot = warp_append(&cb.q_count[1], to_below);
+        if (to_below) {
             if (slot < cb.q_cap) { cb.q1[slot] = c; cb.q1_up[3 * (size_t)slot] = up.max; cb.q1_up[3 * (size_t)slot + 1] = up.dx; cb.q1_up[3 * (size_t)slot + 2] = up.dy; }
             else atomicOr(&cb.live[1], 1u);
+        }
+        const uint32_t slot2 = warp_append(&cb.q_count[2], to_emit);
+        if (to_emit) {
+            if (slot2 < cb.q_cap) {
+                cb.q2[slot2] = c;
+                float* o = cb.q2_scan + 6 * (size_t)slot2;
+                o[0] = up.max; o[1] = up.dx; o[2] = up.dy; o[3] = 0.f; o[4] = 0.f; o[5] = 0.f;      // neutral_scan() below
+            } else atomicOr(&cb.live[1], 1u);
         }
     }
 }
