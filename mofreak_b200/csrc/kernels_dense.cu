@@ -125,13 +125,15 @@ void launch_absdiff(cudaStream_t st, const Geom& g, const uint8_t* store, int st
 // trailing block and of the leftover use the per-pixel function.
 __global__ void k_half(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base, int sw, int spx, int dw, int dh, int dpx) {
     const int f = blockIdx.z;
-    const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int oy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (ox0 >= dw || oy >= dh) return;
+    const int paired_out = ((sw >> 4) >> 1) * 16;                  // columns that follow the uniform rule (a multiple of 16)
+    const int quads = paired_out >> 2;
+    if (oy >= dh) return;
     const uint8_t* src = src_base + (size_t)f * spx;
-    uint8_t* dst = dst_base + (size_t)f * dpx + oy * dw + ox0;
-    const int paired_out = ((sw >> 4) >> 1) * 16;
-    if (ox0 + 3 < paired_out) {
+    uint8_t* row = dst_base + (size_t)f * dpx + oy * dw;
+    if (t < quads) {
+        const int ox0 = 4 * t;
         uint32_t u0, u1, l0, l1;
         load8(src + (2 * oy) * sw + 2 * ox0, u0, u1);
         load8(src + (2 * oy + 1) * sw + 2 * ox0, l0, l1);
@@ -139,9 +141,14 @@ __global__ void k_half(const uint8_t* __restrict__ src_base, uint8_t* __restrict
         // horizontal: avg(v[2j], v[2j+1]) — pair the even and the odd bytes
         const uint32_t ev = __byte_perm(v0, v1, 0x6420), od = __byte_perm(v0, v1, 0x7531);
         const uint32_t r = __vavgu4(ev, od);
-        dst[0] = (uint8_t)r; dst[1] = (uint8_t)(r >> 8); dst[2] = (uint8_t)(r >> 16); dst[3] = (uint8_t)(r >> 24);
+        uint8_t* dst = row + ox0;
+        if (((uintptr_t)dst & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = r;
+        else { dst[0] = (uint8_t)r; dst[1] = (uint8_t)(r >> 8); dst[2] = (uint8_t)(r >> 16); dst[3] = (uint8_t)(r >> 24); }
     } else {
-        for (int k = 0; k < 4 && ox0 + k < dw; k++) dst[k] = (uint8_t)half_px(src, sw, ox0 + k, oy);
+        // the columns of the odd trailing block and of the leftover follow per-column rules: ONE of them per thread, so
+        // that the slow path runs once in the row's last warp instead of four times in a row
+        const int ox = paired_out + (t - quads);
+        if (ox < dw) row[ox] = (uint8_t)half_px(src, sw, ox, oy);
     }
 }
 
@@ -186,7 +193,8 @@ void launch_pyramid(cudaStream_t st, const Geom& g, uint8_t* img) {
             dim3 grid((D.w / 2 + 31) / 32, (D.h / 2 + 7) / 8, g.F);
             k_twothird<<<grid, block, 0, st>>>(img + S.base, img + D.base, S.w, S.px, D.w, D.h, D.px);
         } else {
-            dim3 grid(((D.w + 3) / 4 + 31) / 32, (D.h + 7) / 8, g.F);
+            const int paired_out = ((S.w >> 4) >> 1) * 16;               // one thread per 4 uniform columns, then one per tail column
+            dim3 grid((paired_out / 4 + (D.w - paired_out) + 31) / 32, (D.h + 7) / 8, g.F);
             k_half<<<grid, block, 0, st>>>(img + S.base, img + D.base, S.w, S.px, D.w, D.h, D.px);
         }
     }
