@@ -459,7 +459,7 @@ constexpr int IG_WARPS = 4;
 // one image row of one strip: the lane's four pixels v (packed), the sum of the row left of the strip -> running column sums,
 // transposed through shared memory so that each store instruction covers 128 contiguous bytes
 __device__ __forceinline__ void integral_row(uint32_t v, int left_of_strip, int lane, int& acc0, int& acc1, int& acc2, int& acc3,
-                                             int& left_acc, int32_t* xp, int32_t* o, const bool st0, const bool st1, const bool st2,
+                                             int32_t* xp, int32_t* o, const bool st0, const bool st1, const bool st2,
                                              const bool st3, const bool first_strip) {
     const int p0 = (int)(v & 0xffu), p1 = p0 + (int)((v >> 8) & 0xffu), p2 = p1 + (int)((v >> 16) & 0xffu), p3 = p2 + (int)(v >> 24);
     int incl = p3;
@@ -468,10 +468,9 @@ __device__ __forceinline__ void integral_row(uint32_t v, int left_of_strip, int 
         const int n = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += n;
     }
-    left_acc += left_of_strip;
-    const int before = incl - p3;                                  // row sum left of this lane inside the strip
-    acc0 += before + p0; acc1 += before + p1; acc2 += before + p2; acc3 += before + p3;
-    *reinterpret_cast<int4*>(&xp[4 * lane]) = make_int4(acc0 + left_acc, acc1 + left_acc, acc2 + left_acc, acc3 + left_acc);
+    const int t = incl - p3 + left_of_strip;                      // row sum left of this lane: inside the strip + left of the strip
+    acc0 += t + p0; acc1 += t + p1; acc2 += t + p2; acc3 += t + p3;   // running column sums = the integral itself
+    *reinterpret_cast<int4*>(&xp[4 * lane]) = make_int4(acc0, acc1, acc2, acc3);
     __syncwarp();
     if (st0) o[lane] = xp[lane];
     if (st1) o[32 + lane] = xp[32 + lane];
@@ -505,7 +504,7 @@ k_integral_strips(const uint8_t* __restrict__ img, const int32_t* __restrict__ l
     if (st2) o[64 + lane] = 0;
     if (st3) o[96 + lane] = 0;
     if (first_strip && lane == 0) o[-1] = 0;
-    int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, left_acc = 0;
+    int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
     int32_t* xp = xpose[wib];
     const int W1 = W + 1;
     int y = 0;
@@ -521,14 +520,14 @@ k_integral_strips(const uint8_t* __restrict__ img, const int32_t* __restrict__ l
 #pragma unroll
         for (int k = 0; k < IG_AHEAD; k++) {
             o += W1;
-            integral_row(px[k] & keep, lv[k], lane, acc0, acc1, acc2, acc3, left_acc, xp, o, st0, st1, st2, st3, first_strip);
+            integral_row(px[k] & keep, lv[k], lane, acc0, acc1, acc2, acc3, xp, o, st0, st1, st2, st3, first_strip);
         }
     }
     for (; y < H; y++) {                                                 // the last H % 8 rows
         const uint32_t v = ALIGNED ? *reinterpret_cast<const uint32_t*>(col) : load4(col);
         const int l = *lf;
         col += W; lf += strips; o += W1;
-        integral_row(v & keep, l, lane, acc0, acc1, acc2, acc3, left_acc, xp, o, st0, st1, st2, st3, first_strip);
+        integral_row(v & keep, l, lane, acc0, acc1, acc2, acc3, xp, o, st0, st1, st2, st3, first_strip);
     }
 }
 
