@@ -218,7 +218,11 @@ constexpr int SC_TW = 64, SC_TH = 32;                 // output tile
 constexpr int SC_SW = SC_TW + 8, SC_SH = SC_TH + 6;   // staged: columns x0-4 .. x0+67, rows y0-3 .. y0+34
 constexpr int SC_WORDS = SC_SW / 4;                   // aligned words per staged row
 
-struct ScoreTiles { int first_row[N_LAYERS + 1]; int across[N_LAYERS]; };   // tile-row ranges and tile columns per layer
+struct ScoreTiles {                         // blockIdx.y = tile row over all layers -> its layer and first image row
+    int across[N_LAYERS];
+    uint8_t layer[768];                     // frames up to 8192 rows: 748 tile rows
+    int16_t y0[768];
+};
 
 __global__ void __launch_bounds__(256)
 k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tiles, const uint8_t* __restrict__ img_all,
@@ -227,13 +231,11 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     // grid = (widest layer's tile columns, tile rows of all layers, pairs): no division to find the tile; the blocks
     // beyond a narrower layer's last column leave at once
     const int f = blockIdx.z;
-    int l = 0;
-#pragma unroll
-    for (int k = 1; k < N_LAYERS; k++) l += ((int)blockIdx.y >= tiles.first_row[k]);
+    const int l = tiles.layer[blockIdx.y];
     const int tcol = blockIdx.x;
     if (tcol >= tiles.across[l]) return;
     const LayerGeom& L = g.L[l];
-    const int x0 = tcol * SC_TW, y0 = ((int)blockIdx.y - tiles.first_row[l]) * SC_TH;
+    const int x0 = tcol * SC_TW, y0 = tiles.y0[blockIdx.y];
     const int w = L.w, h = L.h;
     const uint8_t* img = img_all + L.base + (size_t)f * L.px;
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -346,12 +348,10 @@ void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* 
     ScoreTiles tiles;
     int rows = 0, widest = 0;
     for (int l = 0; l < N_LAYERS; l++) {
-        tiles.first_row[l] = rows;
         tiles.across[l] = (g.L[l].w + SC_TW - 1) / SC_TW;
         widest = max(widest, tiles.across[l]);
-        rows += (g.L[l].h + SC_TH - 1) / SC_TH;
+        for (int y = 0; y < g.L[l].h && rows < 768; y += SC_TH, rows++) { tiles.layer[rows] = (uint8_t)l; tiles.y0[rows] = (int16_t)y; }
     }
-    tiles.first_row[N_LAYERS] = rows;
     // gridDim.z <= 65535 pairs per launch sequence (context.cu caps max_pairs far below)
     k_scores<<<dim3(widest, rows, g.F), dim3(32, 8), 0, st>>>(g, tiles, img, S, hitmask, score_mask_words(g.W));
 }
