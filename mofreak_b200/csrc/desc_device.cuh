@@ -181,19 +181,6 @@ __device__ __forceinline__ int resize_px_flat(const uint8_t* __restrict__ roi, c
     return min(max(v, 0), 255);
 }
 
-// the same destination pixel of two regions that share their geometry (frame t and t-5): taps, clamps and offsets once
-__device__ __forceinline__ void resize_px_pair(const uint8_t* __restrict__ roi_a, const uint8_t* __restrict__ roi_b, int stride, int s,
-                                               const ResizeTap ty, const ResizeTap tx, int& va, int& vb) {
-    const int y0 = min(max((int)ty.ofs, 0), s - 1), y1 = min(max((int)ty.ofs + 1, 0), s - 1);
-    const int x0 = tx.xofs, x1 = min(x0 + 1, s - 1);
-    const int o00 = y0 * stride + x0, o01 = y0 * stride + x1, o10 = y1 * stride + x0, o11 = y1 * stride + x1;
-    const int a0 = tx.ax0, a1 = tx.ax1, b0 = ty.by0, b1 = ty.by1;
-    const int Ra0 = roi_a[o00] * a0 + roi_a[o01] * a1, Ra1 = roi_a[o10] * a0 + roi_a[o11] * a1;
-    const int Rb0 = roi_b[o00] * a0 + roi_b[o01] * a1, Rb1 = roi_b[o10] * a0 + roi_b[o11] * a1;
-    va = min(max((((b0 * (Ra0 >> 4)) >> 16) + ((b1 * (Ra1 >> 4)) >> 16) + 2) >> 2, 0), 255);
-    vb = min(max((((b0 * (Rb0 >> 4)) >> 16) + ((b1 * (Rb1 >> 4)) >> 16) + 2) >> 2, 0), 255);
-}
-
 // SSD of motion test (centre c, shift k) on the two 19x19 patches.  Each "3x3 patch" is 9 CONSECUTIVE bytes of
 // the row-major buffer starting at the patch's top-left corner: the reference walks ROI .data linearly
 // (MoFREAKUtilities.cpp:79-88), and that is part of the output contract.  Centres :307-316, shifts :55-70.

@@ -211,9 +211,9 @@ void launch_pyramid(cudaStream_t st, const Geom& g, uint8_t* img) {
 //     min_k v_k - p            = low  half of min_k X_k, minus p
 //     p - max_k v_k            = high half of min_k X_k, minus (255 - p)
 // 16 + 16 packed min3 build all 16 arc minima (windows of 3, then 3 of those), 8 packed max3 reduce them.
-// One launch covers all six layers of all pairs: blockIdx.x enumerates 64x32 tiles over the pair's pyramid,
-// blockIdx.y is the pair.  A block of 256 threads (32 x 8) stages the tile plus its 3-px halo (aligned 32-bit global
-// reads, 128-bit shared stores, 4 packed pixels each) and every thread scores 2 x 4 pixels.
+// One launch covers all six layers of all pairs: grid = (tile column, tile row over all layers, pair) of 64x32 tiles.
+// A block of 256 threads (32 x 8) stages the tile plus its 3-px halo (aligned 32-bit global reads, 128-bit shared
+// stores, 4 packed pixels each) and every thread scores 2 x 4 pixels.
 constexpr int SC_TW = 64, SC_TH = 32;                 // output tile
 constexpr int SC_SW = SC_TW + 8, SC_SH = SC_TH + 6;   // staged: columns x0-4 .. x0+67, rows y0-3 .. y0+34
 constexpr int SC_WORDS = SC_SW / 4;                   // aligned words per staged row

@@ -41,7 +41,8 @@ def test_golden_rows_bit_exact(lib_loaded, orc, name):
 
 
 @pytest.mark.parametrize("shape,frames,seed", [((160, 120), 14, 11), ((320, 240), 9, 12), ((720, 576), 7, 13),
-                                               ((106, 97), 9, 14), ((367, 251), 8, 15), ((48, 48), 8, 16), ((1280, 720), 6, 17)])
+                                               ((106, 97), 9, 14), ((367, 251), 8, 15), ((48, 48), 8, 16), ((1280, 720), 6, 17),
+                                               ((1920, 1080), 6, 18)])
 def test_rows_equal_oracle(orc, shape, frames, seed):
     w, h = shape
     clip = mofreak_b200.synth_clip(w, h, frames, seed)
@@ -233,7 +234,7 @@ def test_full_size_properties_kth_batch():
 
 
 def test_serial_and_pipelined_launch_sequences_agree(orc):
-    """Consecutive launch sequences alternate between two buffer sets on two streams; the rows must not depend on it."""
+    """Consecutive launch sequences rotate through four buffer sets on their own streams; the rows must not depend on it."""
     clip = mofreak_b200.synth_clip(320, 240, 30, 77)
     want = orc.extract_clip(clip)
     with mofreak_b200.Context(320, 240, 30, 4) as ctx:          # 25 pairs -> 7 launch sequences
