@@ -354,6 +354,7 @@ def run_ours(args):
             "rows_per_frame": rows_per_frame,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n_frames * W * H, "d2h_bytes_per_step": int(rows_e2e) * 32,
                     "ms_per_step": ms_e2e / args.steps, "gpu_launches": int(launches_e2e), "contexts": 2,
+                    "h2d_gb_per_s_per_gpu": n_frames * W * H / (ms_e2e / args.steps * 1e-3) / 1e9,
                     "timing": "host clock around the K steps, device synchronised on both sides (every fetch blocks, so "
                               "this bounds the device time from above); steps alternate between two contexts so the "
                               "fetch of step k overlaps the uploads and kernels of step k+1"},
