@@ -199,8 +199,9 @@ def run_ours(args):
     n_frames = STREAMS * FRAMES_PER_STREAM
     n_pairs = STREAMS * PAIRS_PER_STREAM
     # synthetic streams, distinct per rank; pinned so that the e2e upload is a real async DMA
-    host = torch.empty((n_frames, H, W), dtype=torch.uint8, pin_memory=True)
-    hv = host.numpy()
+    # page-locked frames from the library's allocator; --wc asks for write-combined pages (the host only fills them)
+    host = mofreak_b200.HostBuffer(n_frames * H * W, write_combined=args.wc)
+    hv = host.array.reshape(n_frames, H, W)
     for s in range(STREAMS):
         hv[s * FRAMES_PER_STREAM:(s + 1) * FRAMES_PER_STREAM] = mofreak_b200.synth_clip(W, H, FRAMES_PER_STREAM, 1 + rank * STREAMS + s)
     cur = np.concatenate([np.arange(5, FRAMES_PER_STREAM) + s * FRAMES_PER_STREAM for s in range(STREAMS)]).astype(np.int32)
@@ -212,7 +213,7 @@ def run_ours(args):
     rows_host = torch.empty((row_cap, 32), dtype=torch.uint8, pin_memory=True)
 
     # ---- resident: frames already in the HBM frame store ----
-    ctx.upload_raw(host.data_ptr(), n_frames, 0)
+    ctx.upload_raw(host.ptr, n_frames, 0)
     ctx.sync()
 
     def step_resident():
@@ -292,7 +293,7 @@ def run_ours(args):
     def submit_e2e(c):
         c.reset_rows()
         for f0, nf, ps in chunks:
-            c.upload_raw(host.data_ptr() + f0 * frame_bytes, nf, f0)
+            c.upload_raw(host.ptr + f0 * frame_bytes, nf, f0)
             c.extract_pairs(cur[ps], prev[ps], label[ps])
 
     def run_e2e(steps):
@@ -394,6 +395,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS, help="720x576 streams per GPU per step")
     ap.add_argument("--max-pairs", type=int, default=MAX_PAIRS, help="frame pairs per internal launch sequence")
+    ap.add_argument("--wc", type=int, default=0, help="1: write-combined page-locked frame buffer for the end-to-end leg")
     args = ap.parse_args()
     STREAMS, MAX_PAIRS = args.streams, args.max_pairs
     if args.impl == "reference":

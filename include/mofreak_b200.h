@@ -71,6 +71,12 @@ int  mfk_sync(mfk_ctx* ctx);                      /* waits for the context's str
  * slots slot0 .. slot0+n_frames-1 (indices taken modulo store_frames).  Async when `gray` is pinned.
  * Replaces: frame_queue.push(frame.clone()) of MoFREAKUtilities.cpp:391-399, 485-487. */
 int  mfk_upload_frames(mfk_ctx* ctx, const uint8_t* gray, size_t stride, int n_frames, int slot0);
+/* Page-locked HOST memory for frame and row buffers: uploads from it are true asynchronous DMA (pageable memory is
+ * staged by the driver and stalls the caller).  write_combined != 0 asks for write-combined pages: faster for the
+ * device to read, slow for the CPU to read back - for buffers the host only fills (decoded frames).  Portable across
+ * contexts/devices.  No counterpart in the reference (its frames are cv::Mat in pageable memory). */
+int  mfk_host_alloc(void** ptr, size_t bytes, int write_combined);
+int  mfk_host_free(void* ptr);
 /* Frame ingest from interleaved 8-bit BGR: uploads n_frames frames (stride = bytes per source row,
  * >= 3 * width) and converts them to gray ON THE DEVICE into slots slot0.. exactly as cv::cvtColor(CV_BGR2GRAY)
  * does for the reference (MoFREAKUtilities.cpp:395, 410): (B*cb + G*cg + R*cr + half) >> bits.  coeff_bits = 14

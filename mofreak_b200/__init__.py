@@ -6,5 +6,5 @@ BagOfWordsRepresentation call surface).  This package only carries the build rec
 used by the tests and the benchmark.
 """
 from . import build as _build  # noqa: F401
-from .capi import (Context, MofreakError, ROW_DTYPE, FRAME_GAP, SYMBOLS, LIB_PATH, lib, synth_clip,  # noqa: F401
+from .capi import (Context, MofreakError, ROW_DTYPE, FRAME_GAP, SYMBOLS, LIB_PATH, lib, synth_clip, HostBuffer,  # noqa: F401
                    freak_scale_index)

@@ -21,7 +21,7 @@ assert ROW_DTYPE.itemsize == 32
 
 # every symbol include/mofreak_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "mfk_create", "mfk_create_ex", "mfk_destroy", "mfk_last_error", "mfk_sync", "mfk_upload_frames", "mfk_upload_frames_bgr", "mfk_frame_store",
+    "mfk_create", "mfk_create_ex", "mfk_destroy", "mfk_last_error", "mfk_sync", "mfk_host_alloc", "mfk_host_free", "mfk_upload_frames", "mfk_upload_frames_bgr", "mfk_frame_store",
     "mfk_extract_pairs", "mfk_fetch_rows", "mfk_rows_device", "mfk_reset_rows", "mfk_extract_clip", "mfk_rows_text", "mfk_format_rows", "mfk_extract_clip_text", "mfk_mip_describe",
     "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram",
     "mfk_allreduce_counts", "mfk_nccl_unique_id", "mfk_nccl_comm_init", "mfk_nccl_comm_destroy", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read", "mfk_profile_timeline",
@@ -62,6 +62,8 @@ def lib():
     L.mfk_last_error.argtypes = [p]; L.mfk_last_error.restype = C.c_char_p
     L.mfk_sync.argtypes = [p]
     L.mfk_upload_frames.argtypes = [p, u8p, C.c_size_t, C.c_int, C.c_int]
+    L.mfk_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
+    L.mfk_host_free.argtypes = [C.c_void_p]
     L.mfk_upload_frames_bgr.argtypes = [p, u8p, C.c_size_t, C.c_int, C.c_int, C.c_int]
     L.mfk_frame_store.argtypes = [p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     L.mfk_extract_pairs.argtypes = [p, i32p, i32p, i32p, C.c_int]
@@ -102,6 +104,31 @@ def lib():
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class HostBuffer:
+    """Page-locked host memory from mfk_host_alloc as a uint8 numpy array (`.array`); freed on close()/GC."""
+
+    def __init__(self, nbytes, write_combined=False):
+        L = lib()
+        p = C.c_void_p()
+        rc = L.mfk_host_alloc(C.byref(p), nbytes, 1 if write_combined else 0)
+        if rc != MFK_OK:
+            raise MofreakError(rc, (L.mfk_last_error(None) or b"").decode())
+        self._L, self.ptr, self.nbytes = L, p.value, nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self._L.mfk_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def synth_clip(w, h, n_frames, seed, t0=0):

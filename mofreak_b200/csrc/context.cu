@@ -511,6 +511,19 @@ int mfk_sync(mfk_ctx* c) {
     return sync_all(c);
 }
 
+int mfk_host_alloc(void** ptr, size_t bytes, int write_combined) {
+    if (!ptr || bytes == 0) return fail(nullptr, MFK_ERR_ARG, "bad argument to mfk_host_alloc");
+    *ptr = nullptr;
+    const cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0));
+    if (e != cudaSuccess) return fail(nullptr, MFK_ERR_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return MFK_OK;
+}
+
+int mfk_host_free(void* ptr) {
+    if (!ptr) return MFK_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? MFK_OK : MFK_ERR_CUDA;
+}
+
 int mfk_upload_frames(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_frames, int slot0) {
     if (!c || !gray || n_frames < 0 || slot0 < 0) return fail(c, MFK_ERR_ARG, "bad argument to mfk_upload_frames");
     if (stride < (size_t)c->W) return fail(c, MFK_ERR_ARG, "stride %zu < width %d", stride, c->W);

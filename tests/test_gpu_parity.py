@@ -342,3 +342,19 @@ def test_back_to_back_steps_and_interleaved_contexts_agree(orc):
         a.extract_pairs(cur[:2], cur[:2] - 5, cur[:2] - 1)
         a.reset_rows()
         assert a.rows_device()[1] == 0 and a.rows_text() == b""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wc", [False, True])
+def test_host_buffers_from_the_library(wc):
+    clip = mofreak_b200.synth_clip(160, 120, 9, 4)
+    buf = mofreak_b200.HostBuffer(clip.size, write_combined=wc)
+    buf.array[:] = clip.reshape(-1)
+    with mofreak_b200.Context(160, 120, 16, 4) as ctx:
+        want = ctx.extract_clip(clip)
+        ctx.upload_raw(buf.ptr, 9, 0)
+        cur = np.arange(5, 9, dtype=np.int32)
+        ctx.extract_pairs(cur, cur - 5, cur - 1)
+        got, _ = ctx.fetch_rows(len(want) + 8)
+        assert util.rows_equal(got, want) and len(want) > 0
+    buf.close()
