@@ -235,7 +235,7 @@ def run_ours(args):
     launches = ctx.launch_count() - launches0
 
     # ---- per-kernel accounting: same steps with the launch sequences serialised, so that every CUDA-event span is
-    # one kernel family's own time (in the throughput run above two batches overlap on two streams) ----
+    # one kernel family's own time (in the throughput run above four batches overlap on their own streams) ----
     ctx.set_serial(True)
     step_resident(); ctx.sync()
     ctx.profile_enable(True)

@@ -56,7 +56,10 @@ typedef struct mfk_row {
  * store_frames: capacity of the device-resident frame store (the "frame ring"), in frames.
  * max_pairs:    how many (frame t, frame t-5) pairs one internal launch sequence processes.
  * Replaces: new MoFREAKUtilities(dataset) + the per-frame new BriskFeatureDetector(30) / cv::FREAK
- * construction of MoFREAKUtilities.cpp:420-427 (all tables are built once here). */
+ * construction of MoFREAKUtilities.cpp:420-427 (all tables are built once here).
+ * Device memory: the store plus four sets ("lanes") of per-launch-sequence buffers, about 11 MB per pair and set at
+ * 720x576 (27 B per frame pixel), i.e. ~11 GB for max_pairs = 256; the environment variable MFK_LANES = 1..4 lowers
+ * the number of sets (less memory, less overlap between consecutive launch sequences). */
 int  mfk_create(mfk_ctx** out, int device, int width, int height, int store_frames, int max_pairs);
 /* Same, with explicit per-pair budgets (0 = default) for detector candidates and output rows. */
 int  mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_frames, int max_pairs,

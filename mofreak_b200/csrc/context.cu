@@ -2,9 +2,11 @@
 //
 // Device memory of a context (W x H frames, store of N frames, batches of up to F pairs):
 //   frame store            N * W*H                u8     the ring that keeps t and t-5 resident
-//   maps img/S/seen/status 4 * F * pyr_px         u8     layout in geom.h (pyr_px ~ 1.9 W*H)
-//   integral               F * (W+1)(H+1)         i32
-//   candidates             cand_cap * 30 B               ordered list + keypoint records + scans
+//   per lane (x4: consecutive launch sequences rotate through complete buffer sets, each on its own streams)
+//     maps img/S/seen/status 4 * F * pyr_px       u8     layout in geom.h (pyr_px ~ 1.9 W*H)
+//     integral             F * (W+1)(H+1)         i32
+//     hit masks            F * rows * ceil(W/64)  u64    detector hits, one word per (pair, layer row, 64-column tile)
+//     candidates           cand_cap * 30 B               ordered list + keypoint records + scans, work queues, tie lists
 //   rows                   row_cap * 32 B                accumulated mfk_row output
 //   FREAK tables           8.4 MB                        64 x 256 x 43 receptive fields (float x, y, sigma)
 #include <cuda_runtime.h>
@@ -433,6 +435,7 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUC(cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->main_mark, cudaEventDisableTiming));
+    // tuning knob (documented in the header at mfk_create): number of buffer sets, 1..4
     if (const char* e = getenv("MFK_LANES")) c->lanes_built = std::max(1, std::min((int)mfk_ctx::MAX_LANES, atoi(e)));
     c->n_lanes = c->lanes_built;
     for (int li = 0; li < c->lanes_built; li++) {
@@ -465,8 +468,8 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     const size_t scan_n = std::max<size_t>(cand_cap, F * c->rows);
     CUC(dalloc(&c->counters, 8));
     CUC(cudaMemset(c->counters, 0, 8 * sizeof(uint32_t)));
-    // a context that only ever sees one launch sequence per call (max_pairs >= the caller's batches) still gets both
-    // lanes: consecutive calls alternate as well
+    // a context that only ever sees one launch sequence per call (max_pairs >= the caller's batches) still gets all
+    // lanes: consecutive calls rotate through them as well
     for (int li = 0; li < c->lanes_built; li++) {
         mfk_ctx::Lane& L = c->lane[li];
         CUC(dalloc(&L.maps.img, F * c->pyr_px + slack));
