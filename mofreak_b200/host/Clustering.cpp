@@ -20,10 +20,10 @@ struct Lcg15 {
 }  // namespace
 
 Clustering::Clustering(int dim, int num_clust, int num_pts, int num_classes, std::vector<int> poss_classes, std::string svm_path)
-    : DIMENSIONALITY(dim), NUMBER_OF_CLUSTERS(num_clust), NUMBER_OF_POINTS_TO_SAMPLE(num_pts), NUMBER_OF_CLASSES(num_classes),
-      SVM_PATH(svm_path), centers_((size_t)num_clust * dim, 0), data_rows_(0), possible_classes(poss_classes),
-      motion_descriptor_size(0), appearance_descriptor_size(0), motion_is_binary(true), appearance_is_binary(true), center_row(0),
-      seed_(0), shuffles_(0) {}
+    : seed_(0), shuffles_(0), data_rows_(0), centers_((size_t)num_clust * dim, 0), center_row(0), possible_classes(poss_classes),
+      appearance_descriptor_size(0), motion_descriptor_size(0), appearance_is_binary(true), motion_is_binary(true),
+      SVM_PATH(svm_path), DIMENSIONALITY(dim), NUMBER_OF_CLUSTERS(num_clust), NUMBER_OF_POINTS_TO_SAMPLE(num_pts),
+      NUMBER_OF_CLASSES(num_classes) {}
 
 void Clustering::setMotionDescriptor(unsigned int size, bool binary) { motion_descriptor_size = (int)size; motion_is_binary = binary; }
 void Clustering::setAppearanceDescriptor(unsigned int size, bool binary) { appearance_descriptor_size = (int)size; appearance_is_binary = binary; }

@@ -14,39 +14,34 @@
 
 class Clustering {
 public:
+    // ---- extensions (not in the reference) ----
+    // 0 (default) = the reference's behaviour, srand(time(NULL)) at every shuffle; any other value makes the selection reproducible
+    void setSeed(uint32_t seed) { seed_ = seed; }
+    const std::vector<uint8_t>& centers() const { return centers_; }      // num_clust x dim bytes, row-major
+    int centersFilled() const { return center_row; }
+
+    // ---- the reference's surface (Clustering.h:15-27), same names, argument order and meaning ----
     Clustering(int dim, int num_clust, int num_pts, int num_classes, std::vector<int> poss_classes, std::string svm_path);
-    // rows = 3 metadata bytes (action, person, video_number) + appearance bytes + motion bytes (Clustering.cpp:57-116)
+    void setAppearanceDescriptor(unsigned int size, bool binary);
+    void setMotionDescriptor(unsigned int size, bool binary);
+    // one data row per feature: action, person, video_number, then the appearance and the motion bytes (Clustering.cpp:57-116)
     void buildDataFromMoFREAK(std::deque<MoFREAKFeature> mofreak_ftrs, bool sample_pts, bool img_diff = false, bool fix_class = false,
                               int fixed_class = 1);
     void randomClusters(bool only_one_class = false);     // Clustering.cpp:165-213
     void writeClusters(bool append = false);              // Clustering.cpp:233-257
-    void setMotionDescriptor(unsigned int size, bool binary);
-    void setAppearanceDescriptor(unsigned int size, bool binary);
-
-    // --- not in the reference ---
-    // 0 (default) = the reference's behaviour, srand(time(NULL)) at every shuffle; any other value makes the selection reproducible
-    void setSeed(uint32_t seed) { seed_ = seed; }
-    const std::vector<uint8_t>& centers() const { return centers_; }      // NUMBER_OF_CLUSTERS x DIMENSIONALITY
-    int centersFilled() const { return center_row; }
 
 private:
     void shuffleRows(std::vector<uint8_t>& mx, int cols);
 
-    const int DIMENSIONALITY;
-    const int NUMBER_OF_CLUSTERS;
-    const int NUMBER_OF_POINTS_TO_SAMPLE;
-    const int NUMBER_OF_CLASSES;
-    const std::string SVM_PATH;
-
-    std::vector<uint8_t> centers_;
-    std::vector<uint8_t> data_pts_;      // rows x (DIMENSIONALITY + 3)
-    int data_rows_;
-    std::vector<int> possible_classes;
-    int motion_descriptor_size;
-    int appearance_descriptor_size;
-    bool motion_is_binary;
-    bool appearance_is_binary;
-    int center_row;
     uint32_t seed_;
     uint32_t shuffles_;                  // distinguishes the shuffles of one seeded run
+    std::vector<uint8_t> data_pts_;      // data_rows_ x (DIMENSIONALITY + 3) bytes
+    int data_rows_;
+    std::vector<uint8_t> centers_;
+    int center_row;                      // next free codeword; classes append one after the other
+    std::vector<int> possible_classes;
+    int appearance_descriptor_size, motion_descriptor_size;
+    bool appearance_is_binary, motion_is_binary;
+    const std::string SVM_PATH;
+    const int DIMENSIONALITY, NUMBER_OF_CLUSTERS, NUMBER_OF_POINTS_TO_SAMPLE, NUMBER_OF_CLASSES;
 };
