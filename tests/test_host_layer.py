@@ -220,3 +220,19 @@ def test_host_class_grows_device_budgets_for_busy_frames(host, orc, tmp_path):
     want = orc.extract_clip(frames)
     assert n == len(want)
     assert out.read_text() == orc.format_mofreak(want)
+
+
+def test_command_line_cluster_stage(tmp_path):
+    exe = os.path.join(HOST_DIR, "mofreak_main")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", HOST_DIR], check=True)
+    a = tmp_path / "a.mofreak"; a.write_text(util.golden_text("kth_160x120x100_seed1"))
+    b = tmp_path / "b.mofreak"; b.write_text(util.golden_text("ucf_320x240x12_seed3"))
+    args = [exe, "cluster", "KTH", "10", "2", str(tmp_path), "5", "1:%s" % a, "2:%s" % b]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    first = (tmp_path / "clusters.txt").read_text()
+    lines = [l for l in first.split("\n") if l]
+    assert len(lines) == 10 and all(len(l.split()) == 16 and l.endswith(" ") for l in lines)
+    subprocess.run(args, capture_output=True, text=True, check=True)
+    assert (tmp_path / "clusters.txt").read_text() == first                      # seeded: reproducible

@@ -145,3 +145,19 @@ def test_gpu_clip_text_is_the_golden_file(name):
         got, _ = ctx.fetch_rows(1 << 16)
         assert t.decode() == python_text(got) and len(got) > 0
         assert ctx.rows_text() == b""
+
+
+def test_percent_g_whole_float_space_is_exact_or_refused():
+    """Any bit pattern: either the formatter refuses (exponent notation / non-finite -> host fallback) or its text is glibc's."""
+    rng = np.random.default_rng(11)
+    bits = rng.integers(0, 2**32, 100000, dtype=np.uint64).astype(np.uint32)
+    refused = 0
+    for v in bits.view(np.float32):
+        got = harness_float(float(v))
+        if got is None:
+            refused += 1
+            want = "%g" % float(v)
+            assert ("e" in want) or ("n" in want) or float(v) == np.float32(1e-4), (v, want)      # inf/nan, exponent form, or the one float just below 1e-4
+        else:
+            assert got == "%g" % float(v), v
+    assert 0 < refused < len(bits)
