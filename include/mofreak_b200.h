@@ -109,6 +109,9 @@ int  mfk_fetch_rows(mfk_ctx* ctx, mfk_row* rows, size_t cap, size_t* n_rows,
                     uint32_t* rows_per_pair, size_t pairs_cap);
 /* Device-side view of the accumulated rows (valid until the next extract/fetch/reset); syncs. */
 int  mfk_rows_device(mfk_ctx* ctx, const mfk_row** device_rows, size_t* n_rows);
+/* Drops the accumulated rows.  Does not wait: the reset takes effect in stream order just before the next launch
+ * sequence appends its rows (so the front of that sequence may already run under the tail of the previous one), or
+ * at the next call that reads the accumulation.  Rows fetched earlier are unaffected. */
 int  mfk_reset_rows(mfk_ctx* ctx);
 
 /* Whole clip from HOST frames, the shape of one computeMoFREAKFromFile call
