@@ -30,10 +30,12 @@ extern "C" {
 #define MFK_OK              0
 #define MFK_ERR_ARG        -1   /* bad argument */
 #define MFK_ERR_CUDA       -2   /* a CUDA call failed (message has the CUDA error string) */
-#define MFK_ERR_CAPACITY   -3   /* a per-frame candidate/row budget overflowed; recreate with mfk_create_ex */
+#define MFK_ERR_CAPACITY   -3   /* a CALLER buffer is too small; the call says how much is needed, device state is kept */
 #define MFK_ERR_NOMEM      -4
 #define MFK_ERR_STATE      -5   /* call out of order (e.g. fetch before extract) */
 #define MFK_ERR_RANGE      -6   /* a value the device formatter does not cover (see mfk_rows_text) */
+#define MFK_ERR_BUDGET     -7   /* a DEVICE per-pair candidate/row budget overflowed: results of the run are void and
+                                   no sizes are reported; recreate the context with mfk_create_ex and larger budgets */
 
 #define MFK_FRAME_GAP       5
 
@@ -98,13 +100,14 @@ int  mfk_frame_store(mfk_ctx* ctx, uint8_t** device_base, int* store_frames);
  * (BRISK layer-major, raster within a layer, minus FREAK's border drops).  Async.
  * Replaces the loop body of MoFREAKUtilities::computeMoFREAKFromFile, MoFREAKUtilities.cpp:413-483:
  * absdiff, BriskFeatureDetector::detect (brisk.cpp:549-704), cv::FREAK::compute,
- * extractMotionByMotionInterchangePatterns (:288-325) and row assembly (:447-480). */
+ * extractMotionByMotionInterchangePatterns (:288-325) and row assembly (:447-480).
+ * Slots must be >= 0 (taken modulo store_frames); MFK_ERR_ARG otherwise. */
 int  mfk_extract_pairs(mfk_ctx* ctx, const int32_t* cur_slot, const int32_t* prev_slot,
                        const int32_t* label, int n_pairs);
 /* Waits, then copies the rows accumulated since the last fetch/reset to HOST memory.
  * rows_per_pair (optional, may be NULL) receives one count per queued pair, in queue order, at most
  * pairs_cap entries.  *n_rows is the total; if it exceeds cap only cap rows are copied and
- * MFK_ERR_CAPACITY is returned.  Resets the accumulation. */
+ * MFK_ERR_CAPACITY is returned.  MFK_ERR_BUDGET if a device budget overflowed (rows incomplete).  Resets the accumulation. */
 int  mfk_fetch_rows(mfk_ctx* ctx, mfk_row* rows, size_t cap, size_t* n_rows,
                     uint32_t* rows_per_pair, size_t pairs_cap);
 /* Device-side view of the accumulated rows (valid until the next extract/fetch/reset); syncs. */
@@ -135,7 +138,9 @@ int  mfk_format_rows(mfk_ctx* ctx, const mfk_row* rows, size_t n, char* text, si
 /* mfk_extract_clip that also returns the clip's `.mofreak` text: one call = one computeMoFREAKFromFile
  * (MoFREAKUtilities.cpp:374-498 incl. the write at :490-491).  rows may be NULL when only the text is wanted.
  * If the text or the rows do not fit, *n_bytes / *n_rows hold the sizes needed, MFK_ERR_CAPACITY is returned and
- * the accumulation is KEPT: read it with mfk_rows_text + mfk_fetch_rows into larger buffers.  Otherwise resets. */
+ * the accumulation is KEPT: read it with mfk_rows_text + mfk_fetch_rows into larger buffers.  Otherwise resets.
+ * MFK_ERR_BUDGET (a device budget overflowed): *n_bytes = *n_rows = 0, the accumulation is dropped; redo the clip on a
+ * context with larger budgets (mfk_create_ex). */
 int  mfk_extract_clip_text(mfk_ctx* ctx, const uint8_t* gray, size_t stride, int n_frames,
                            char* text, size_t text_cap, size_t* n_bytes,
                            mfk_row* rows, size_t cap, size_t* n_rows);
@@ -155,7 +160,7 @@ int  mfk_bow_set_codebook(mfk_ctx* ctx, const uint8_t* codewords, int K);
 /* desc: N x 16 HOST bytes -> idx: N HOST int32, arg-min Hamming distance, lowest index on ties.
  * Replaces BagOfWordsRepresentation::bruteForceMatch / hammingDistance, :22-72. */
 int  mfk_bow_assign(mfk_ctx* ctx, const uint8_t* desc, size_t N, int32_t* idx);
-/* Same on DEVICE buffers (async). */
+/* Same on DEVICE buffers (async).  d_desc must be 16-byte aligned (descriptors are read as 128-bit words). */
 int  mfk_bow_assign_device(mfk_ctx* ctx, const uint8_t* d_desc, size_t N, int32_t* d_idx);
 /* Assigns the rows currently accumulated on the device (descriptor = appearance|motion) and adds
  * the per-word counts into counts[K] (HOST uint32, overwritten).  The float normalisation of
@@ -167,6 +172,11 @@ int  mfk_bow_histogram(mfk_ctx* ctx, const uint8_t* desc, size_t N, uint32_t* co
  * over all ranks of `nccl_comm` (an ncclComm_t) on the context's stream.  Async.  Returns
  * MFK_ERR_STATE when the library was built without NCCL.  No counterpart in the reference. */
 int  mfk_allreduce_counts(mfk_ctx* ctx, uint32_t* d_counts, size_t n, void* nccl_comm);
+/* mfk_bow_histogram_rows for a video whose rows are spread over the ranks of `nccl_comm`: every rank assigns its own
+ * accumulated rows, the count vectors are summed over the ranks (ncclAllReduce, uint32 sum, NVLink/NVSwitch) and every
+ * rank receives the video's total counts[K] (HOST).  Assignment kernel, collective and read-back are queued back to
+ * back on the context's stream; the host waits once.  Collective: every rank of the communicator must call it. */
+int  mfk_bow_histogram_rows_reduced(mfk_ctx* ctx, uint32_t* counts, void* nccl_comm);
 
 /* Helpers to build the communicator for mfk_allreduce_counts without linking NCCL (same run-time resolution): rank 0 calls
  * mfk_nccl_unique_id and ships the 128 bytes to the other ranks by any means (torch.distributed, MPI, a file); every rank
@@ -175,49 +185,17 @@ int  mfk_nccl_unique_id(uint8_t id_out[128]);
 int  mfk_nccl_comm_init(mfk_ctx* ctx, void** nccl_comm_out, int n_ranks, int rank, const uint8_t id[128]);
 int  mfk_nccl_comm_destroy(void* nccl_comm);
 
-/* ---- measurement ------------------------------------------------------------------------------------ */
+/* ---- utilities ---------------------------------------------------------------------------------------- */
 
-/* CUDA-event stopwatch on the context's stream (torch.cuda.Event only sees torch's own streams). */
-int  mfk_timer_start(mfk_ctx* ctx);
-int  mfk_timer_stop(mfk_ctx* ctx, float* elapsed_ms);   /* syncs */
-/* Per-kernel accounting.  enable != 0 brackets every kernel launch with events from then on.
- * mfk_profile_read syncs and returns, per kernel family, launches and total device ms since enable. */
-#define MFK_PROF_MAX 16
-typedef struct mfk_prof_entry { const char* name; uint32_t launches; float total_ms; } mfk_prof_entry;
-int  mfk_profile_enable(mfk_ctx* ctx, int enable);
-int  mfk_profile_read(mfk_ctx* ctx, mfk_prof_entry* entries, int cap, int* n_entries);
-/* Timeline of the spans recorded since mfk_profile_enable and not yet consumed by mfk_profile_read: one entry per
- * launcher call (kernel family), start/end in device ms relative to the last mfk_timer_start.  With the lanes overlapping
- * this is the Gantt chart of the launch sequences (the reference has no tracing).  Syncs. */
-typedef struct mfk_span { const char* name; float start_ms, end_ms; } mfk_span;
-int  mfk_profile_timeline(mfk_ctx* ctx, mfk_span* spans, int cap, int* n_spans);
-/* serial != 0: consecutive launch sequences no longer overlap (one buffer set, the integral image on the main stream).
- * Throughput runs leave this off; the per-kernel accounting of mfk_profile_* is only a kernel's own time when it is on. */
-int  mfk_set_serial(mfk_ctx* ctx, int serial);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t mfk_launch_count(const mfk_ctx* ctx);
-
-/* ---- stage access for parity tests (device -> host copies of intermediates of the LAST batch) ------- */
-/* what: 0 = pyramid image, 1 = score map S_full; layer 0..5; pair index within the last batch.
- * out must hold the layer's width*height bytes; dims (optional) receives {width, height}. */
-int  mfk_debug_layer(mfk_ctx* ctx, int what, int layer, int pair, uint8_t* out, int* dims);
-/* Keypoints of pair `pair` of the last batch BEFORE FREAK's border filter: n x {x, y, size, response,
- * layer} floats in reference order; writes at most cap, *n gets the full count. */
-int  mfk_debug_keypoints(mfk_ctx* ctx, int pair, float* out, int cap, int* n);
-
-/* Raw device counters of the context: [0] overflow flags, [1] rows accumulated, [2] pairs accumulated, [3] live candidates of
- * the last batch, [4..7] optional statistics (builds with -DMFK_PB_STATS: tie-resolution rounds, ties, max rounds, tie visits). */
-int  mfk_debug_counters(mfk_ctx* ctx, uint32_t out[8]);
-
-/* ---- utilities that are not device work ------------------------------------------------------------- */
-
-/* Deterministic synthetic "moving squares" clip (tests, smoke, bench): n_frames of w x h starting at
- * time t0, see mofreak_b200/host/synth.cpp. */
-void mfk_synth_clip(uint8_t* out, int w, int h, int n_frames, uint32_t seed, int t0);
-/* FREAK scale index of a keypoint size through the context-independent threshold table the device
- * uses (exposed so tests can compare it with the libm expression it was derived from). */
-int  mfk_freak_scale_index(float kp_size);
+/* CUDA-event stopwatch on the context's streams (the reference times a stage with one clock() pair, main.cpp:929-1011). */
+int  mfk_timer_start(mfk_ctx* ctx);
+int  mfk_timer_stop(mfk_ctx* ctx, float* elapsed_ms);   /* syncs */
 const char* mfk_version(void);
+
+/* Per-kernel accounting, stage dumps for parity tests and the synthetic clip generator are declared in
+ * mofreak_b200_debug.h: they are test and measurement instruments, not part of the drop-in surface. */
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmofreak_b200.so")
 
 CU_SOURCES = ["context.cu", "kernels_dense.cu", "kernels_sparse.cu", "kernels_desc.cu", "kernels_bow.cu", "kernels_text.cu"]
-CPP_SOURCES = [os.path.join(CSRC, "tables.cpp"), os.path.join(HERE, "host", "synth.cpp")]
+CPP_SOURCES = [os.path.join(CSRC, "tables.cpp")]
+SYNTH_SRC = os.path.join(HERE, "synth", "synth.cpp")
+SYNTH_LIB = os.path.join(HERE, "synth", "libmofreak_synth.so")      # plain C++, no CUDA: frames for tests/bench
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -40,11 +42,21 @@ def needs_build():
     built = os.path.getmtime(LIB)
     deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     deps.append(os.path.join(HERE, "..", "include", "mofreak_b200.h"))
+    deps.append(os.path.join(HERE, "..", "include", "mofreak_b200_debug.h"))
     return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build_synth(force=False):
+    if not force and os.path.exists(SYNTH_LIB) and os.path.getmtime(SYNTH_LIB) >= os.path.getmtime(SYNTH_SRC):
+        return SYNTH_LIB
+    host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([host_cxx, "-O2", "-std=c++14", "-fPIC", "-shared", "-o", SYNTH_LIB, SYNTH_SRC], check=True)
+    return SYNTH_LIB
 
 
 def build(force=False, verbose=False, extra=()):
     """Compile if sources are newer than the library.  Returns the library path."""
+    build_synth(force)
     if not force and not needs_build():
         return LIB
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

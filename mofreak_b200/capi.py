@@ -12,20 +12,23 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmofreak_b200.so")
 
-MFK_OK, MFK_ERR_ARG, MFK_ERR_CUDA, MFK_ERR_CAPACITY, MFK_ERR_NOMEM, MFK_ERR_STATE = 0, -1, -2, -3, -4, -5
+MFK_OK, MFK_ERR_ARG, MFK_ERR_CUDA, MFK_ERR_CAPACITY, MFK_ERR_NOMEM, MFK_ERR_STATE, MFK_ERR_RANGE, MFK_ERR_BUDGET = 0, -1, -2, -3, -4, -5, -6, -7
 FRAME_GAP = 5
 
 ROW_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("frame", "<i4"), ("scale", "<f4"),
                       ("appearance", "u1", (8,)), ("motion", "u1", (8,))])
 assert ROW_DTYPE.itemsize == 32
 
-# every symbol include/mofreak_b200.h declares (tests check that the library exports all of them)
+SYNTH_LIB_PATH = os.path.join(HERE, "synth", "libmofreak_synth.so")
+
+# every symbol include/mofreak_b200.h (the drop-in surface) and include/mofreak_b200_debug.h (test and measurement
+# instruments) declare; tests check that the library exports all of them
 SYMBOLS = [
     "mfk_create", "mfk_create_ex", "mfk_destroy", "mfk_last_error", "mfk_sync", "mfk_host_alloc", "mfk_host_free", "mfk_upload_frames", "mfk_upload_frames_bgr", "mfk_frame_store",
     "mfk_extract_pairs", "mfk_fetch_rows", "mfk_rows_device", "mfk_reset_rows", "mfk_extract_clip", "mfk_rows_text", "mfk_format_rows", "mfk_extract_clip_text", "mfk_mip_describe",
-    "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram",
+    "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram", "mfk_bow_histogram_rows_reduced",
     "mfk_allreduce_counts", "mfk_nccl_unique_id", "mfk_nccl_comm_init", "mfk_nccl_comm_destroy", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read", "mfk_profile_timeline",
-    "mfk_set_serial", "mfk_launch_count", "mfk_debug_layer", "mfk_debug_keypoints", "mfk_debug_counters", "mfk_synth_clip", "mfk_freak_scale_index", "mfk_version",
+    "mfk_set_serial", "mfk_launch_count", "mfk_debug_layer", "mfk_debug_keypoints", "mfk_debug_counters", "mfk_freak_scale_index", "mfk_version",
 ]
 
 
@@ -81,6 +84,7 @@ def lib():
     L.mfk_bow_assign_device.argtypes = [p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.mfk_bow_histogram_rows.argtypes = [p, u32p]
     L.mfk_bow_histogram.argtypes = [p, u8p, C.c_size_t, u32p]
+    L.mfk_bow_histogram_rows_reduced.argtypes = [p, u32p, C.c_void_p]
     L.mfk_allreduce_counts.argtypes = [p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.mfk_nccl_unique_id.argtypes = [C.c_void_p]
     L.mfk_nccl_comm_init.argtypes = [p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
@@ -95,7 +99,6 @@ def lib():
     L.mfk_debug_layer.argtypes = [p, C.c_int, C.c_int, C.c_int, u8p, C.POINTER(C.c_int)]
     L.mfk_debug_keypoints.argtypes = [p, C.c_int, f32p, C.c_int, C.POINTER(C.c_int)]
     L.mfk_debug_counters.argtypes = [p, C.c_void_p]
-    L.mfk_synth_clip.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int]; L.mfk_synth_clip.restype = None
     L.mfk_freak_scale_index.argtypes = [C.c_float]
     L.mfk_version.restype = C.c_char_p
     _lib = L
@@ -131,10 +134,21 @@ class HostBuffer:
             pass
 
 
+_synth = None
+
+
 def synth_clip(w, h, n_frames, seed, t0=0):
-    """Deterministic "moving squares" clip, uint8 [n_frames, h, w] (mofreak_b200/host/synth.cpp)."""
+    """Deterministic "moving squares" clip, uint8 [n_frames, h, w] (mofreak_b200/synth/synth.cpp).  Lives in its own
+    library (no CUDA), so generating frames does not map the product library into the calling process."""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise ImportError("%s is missing: run `python -m mofreak_b200.build`" % SYNTH_LIB_PATH)
+        _synth = C.CDLL(SYNTH_LIB_PATH)
+        _synth.mfk_synth_clip.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int]
+        _synth.mfk_synth_clip.restype = None
     out = np.empty((n_frames, h, w), np.uint8)
-    lib().mfk_synth_clip(_ptr(out), w, h, n_frames, C.c_uint32(seed), t0)
+    _synth.mfk_synth_clip(_ptr(out), w, h, n_frames, C.c_uint32(seed), t0)
     return out
 
 
@@ -298,6 +312,12 @@ class Context:
     def bow_histogram_rows(self):
         counts = np.zeros(self.K, np.uint32)
         self._check(self._L.mfk_bow_histogram_rows(self._h, _ptr(counts)))
+        return counts
+
+    def bow_histogram_rows_reduced(self, comm):
+        """Counts of this rank's accumulated rows summed over all ranks of `comm` (collective)."""
+        counts = np.zeros(self.K, np.uint32)
+        self._check(self._L.mfk_bow_histogram_rows_reduced(self._h, _ptr(counts), comm))
         return counts
 
     # --- multi-GPU exchange of word counts ---

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/mofreak_b200.h"
+#include "../../include/mofreak_b200_debug.h"
 #include "kernels.h"
 
 using namespace mfk;
@@ -455,6 +456,11 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     c->lw[1] = 2 * (width / 3); c->lh[1] = 2 * (height / 3);
     for (int l = 2; l < N_LAYERS; l++) { c->lw[l] = c->lw[l - 2] / 2; c->lh[l] = c->lh[l - 2] / 2; }
     for (int l = 0; l < N_LAYERS; l++) { c->rows += c->lh[l]; c->pyr_px += c->lw[l] * c->lh[l]; }
+    if (score_tile_rows(c->lh) > score_tile_rows_max()) {      // cannot happen for heights <= 8192; refuse rather than truncate
+        fail(nullptr, MFK_ERR_ARG, "frame height %d needs more score-kernel tile rows than the launch table holds", height);
+        destroy(c);
+        return MFK_ERR_ARG;
+    }
     c->cand_cap_pair = cand_cap_pair > 0 ? cand_cap_pair : std::max(4096, c->pyr_px / 6);
     c->row_cap_pair = row_cap_pair > 0 ? row_cap_pair : std::max(1024, c->pyr_px / 48);
     const size_t F = (size_t)max_pairs;
@@ -600,6 +606,8 @@ int mfk_frame_store(mfk_ctx* c, uint8_t** device_base, int* store_frames) {
 int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_slot, const int32_t* label, int n_pairs) {
     if (!c || n_pairs < 0 || (n_pairs && (!cur_slot || !prev_slot || !label))) return fail(c, MFK_ERR_ARG, "bad argument to mfk_extract_pairs");
     if (n_pairs == 0) return MFK_OK;
+    for (int i = 0; i < n_pairs; i++)
+        if (cur_slot[i] < 0 || prev_slot[i] < 0) return fail(c, MFK_ERR_ARG, "pair %d names a negative store slot", i);
     CU(c, cudaSetDevice(c->device));
     int rc = grow_pair_rows(c, c->pairs_queued + (size_t)n_pairs);
     if (rc != MFK_OK) return rc;
@@ -665,7 +673,7 @@ int mfk_rows_device(mfk_ctx* c, const mfk_row** device_rows, size_t* n_rows) {
     if (rc != MFK_OK) return rc;
     if (device_rows) *device_rows = c->rows_buf;
     if (n_rows) *n_rows = h[1];
-    if (h[0]) return fail(c, MFK_ERR_CAPACITY, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
+    if (h[0]) return fail(c, MFK_ERR_BUDGET, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
                           (h[0] & 1) ? "candidates " : "", (h[0] & 2) ? "rows" : "");
     return MFK_OK;
 }
@@ -687,7 +695,7 @@ int mfk_fetch_rows(mfk_ctx* c, mfk_row* rows, size_t cap, size_t* n_rows, uint32
     const uint32_t overflow = h[0];
     rc = mfk_reset_rows(c);
     if (rc != MFK_OK) return rc;
-    if (overflow) return fail(c, MFK_ERR_CAPACITY, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
+    if (overflow) return fail(c, MFK_ERR_BUDGET, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
                               (overflow & 1) ? "candidates " : "", (overflow & 2) ? "rows" : "");
     if (n > cap) return fail(c, MFK_ERR_CAPACITY, "%zu rows do not fit the caller's buffer of %zu", n, cap);
     return MFK_OK;
@@ -699,7 +707,7 @@ int mfk_rows_text(mfk_ctx* c, char* text, size_t cap, size_t* n_bytes) {
     uint32_t h[4];
     int rc = read_counters(c, h);
     if (rc != MFK_OK) return rc;
-    if (h[0]) return fail(c, MFK_ERR_CAPACITY, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
+    if (h[0]) return fail(c, MFK_ERR_BUDGET, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
                           (h[0] & 1) ? "candidates " : "", (h[0] & 2) ? "rows" : "");
     return format_device_rows(c, c->rows_buf, h[1], text, cap, n_bytes);
 }
@@ -737,12 +745,12 @@ int mfk_extract_clip_text(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_
     uint32_t h[4];
     rc = read_counters(c, h);
     if (rc != MFK_OK) return rc;
-    if (n_rows) *n_rows = h[1];
-    if (h[0]) {
+    if (h[0]) {                    // sizes of an overflowed run mean nothing: report none, so that no caller re-reads it
         mfk_reset_rows(c);
-        return fail(c, MFK_ERR_CAPACITY, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
+        return fail(c, MFK_ERR_BUDGET, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
                     (h[0] & 1) ? "candidates " : "", (h[0] & 2) ? "rows" : "");
     }
+    if (n_rows) *n_rows = h[1];
     const int rc_text = format_device_rows(c, c->rows_buf, h[1], text, text_cap, n_bytes);
     if (rc_text != MFK_OK && rc_text != MFK_ERR_RANGE) return rc_text;       // a text buffer too small keeps the accumulation
     if (rows && h[1] > cap)
@@ -824,8 +832,8 @@ int mfk_bow_assign_device(mfk_ctx* c, const uint8_t* d_desc, size_t N, int32_t* 
     if (!c || (N && (!d_desc || !d_idx))) return fail(c, MFK_ERR_ARG, "bad argument to mfk_bow_assign_device");
     if (!c->codebook) return fail(c, MFK_ERR_STATE, "no codebook set");
     CU(c, cudaSetDevice(c->device));
-    { Span s(c, P_BOW, 1); launch_bow_assign(c->stream, d_desc, 16, N, c->codebook, c->K, d_idx, nullptr); }
-    CU(c, cudaGetLastError());
+    if (((uintptr_t)d_desc & 15) != 0) return fail(c, MFK_ERR_ARG, "d_desc must be 16-byte aligned (descriptors are read as 128-bit words)");
+    { Span s(c, P_BOW, 1); CU(c, launch_bow_assign(c->stream, d_desc, 16, N, nullptr, c->codebook, c->K, d_idx, nullptr)); }
     return MFK_OK;
 }
 
@@ -839,7 +847,7 @@ int mfk_bow_assign(mfk_ctx* c, const uint8_t* desc, size_t N, int32_t* idx) {
     uint8_t* d_desc = (uint8_t*)c->bow_tmp;
     int32_t* d_idx = (int32_t*)((uint8_t*)c->bow_tmp + N * 16);
     CU(c, cudaMemcpyAsync(d_desc, desc, N * 16, cudaMemcpyHostToDevice, c->stream));
-    { Span s(c, P_BOW, 1); launch_bow_assign(c->stream, d_desc, 16, N, c->codebook, c->K, d_idx, nullptr); }
+    { Span s(c, P_BOW, 1); CU(c, launch_bow_assign(c->stream, d_desc, 16, N, nullptr, c->codebook, c->K, d_idx, nullptr)); }
     CU(c, cudaMemcpyAsync(idx, d_idx, N * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return MFK_OK;
@@ -854,10 +862,31 @@ int mfk_bow_histogram(mfk_ctx* c, const uint8_t* desc, size_t N, uint32_t* count
         int rc = ensure_bow_tmp(c, N * 16);
         if (rc != MFK_OK) return rc;
         CU(c, cudaMemcpyAsync(c->bow_tmp, desc, N * 16, cudaMemcpyHostToDevice, c->stream));
-        { Span s(c, P_BOW, 1); launch_bow_assign(c->stream, (const uint8_t*)c->bow_tmp, 16, N, c->codebook, c->K, nullptr, c->bow_counts); }
+        { Span s(c, P_BOW, 1); CU(c, launch_bow_assign(c->stream, (const uint8_t*)c->bow_tmp, 16, N, nullptr, c->codebook, c->K, nullptr, c->bow_counts)); }
     }
     CU(c, cudaMemcpyAsync(counts, c->bow_counts, (size_t)c->K * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    return MFK_OK;
+}
+
+// Counts of the accumulated rows into c->bow_counts (device), queued on the main stream without a host round trip: the
+// kernel takes the live row count from the device counters.  finish_counts() reads counts and overflow flags back.
+static int histogram_rows_device(mfk_ctx* c) {
+    { const int rc = settle(c); if (rc != MFK_OK) return rc; }
+    CU(c, cudaMemsetAsync(c->bow_counts, 0, (size_t)c->K * 4, c->stream));
+    Span s(c, P_BOW, 1);
+    // descriptor = appearance | motion = bytes 16..31 of each 32-byte row
+    CU(c, launch_bow_assign(c->stream, (const uint8_t*)c->rows_buf + 16, 32, c->row_cap, c->counters + 1, c->codebook, c->K, nullptr, c->bow_counts));
+    return MFK_OK;
+}
+
+static int finish_counts(mfk_ctx* c, uint32_t* counts) {
+    uint32_t h[4] = {0, 0, 0, 0};
+    CU(c, cudaMemcpyAsync(counts, c->bow_counts, (size_t)c->K * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(h, c->counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (h[0]) return fail(c, MFK_ERR_BUDGET, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
+                          (h[0] & 1) ? "candidates " : "", (h[0] & 2) ? "rows" : "");
     return MFK_OK;
 }
 
@@ -865,18 +894,8 @@ int mfk_bow_histogram_rows(mfk_ctx* c, uint32_t* counts) {
     if (!c || !counts) return fail(c, MFK_ERR_ARG, "bad argument to mfk_bow_histogram_rows");
     if (!c->codebook) return fail(c, MFK_ERR_STATE, "no codebook set");
     CU(c, cudaSetDevice(c->device));
-    uint32_t h[4];
-    int rc = read_counters(c, h);
-    if (rc != MFK_OK) return rc;
-    CU(c, cudaMemsetAsync(c->bow_counts, 0, (size_t)c->K * 4, c->stream));
-    if (h[1]) {
-        Span s(c, P_BOW, 1);
-        // descriptor = appearance | motion = bytes 16..31 of each 32-byte row
-        launch_bow_assign(c->stream, (const uint8_t*)c->rows_buf + 16, 32, h[1], c->codebook, c->K, nullptr, c->bow_counts);
-    }
-    CU(c, cudaMemcpyAsync(counts, c->bow_counts, (size_t)c->K * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    return MFK_OK;
+    { const int rc = histogram_rows_device(c); if (rc != MFK_OK) return rc; }
+    return finish_counts(c, counts);
 }
 
 // NCCL is resolved at run time so that the library loads on machines without it and shares the copy a host
@@ -905,6 +924,16 @@ int mfk_allreduce_counts(mfk_ctx* c, uint32_t* d_counts, size_t n, void* nccl_co
     const int r = fn(d_counts, d_counts, n, ncclUint32, ncclSum, nccl_comm, c->stream);
     if (r != 0) return fail(c, MFK_ERR_CUDA, "ncclAllReduce failed with code %d", r);
     return MFK_OK;
+}
+
+int mfk_bow_histogram_rows_reduced(mfk_ctx* c, uint32_t* counts, void* nccl_comm) {
+    if (!c || !counts || !nccl_comm) return fail(c, MFK_ERR_ARG, "bad argument to mfk_bow_histogram_rows_reduced");
+    if (!c->codebook) return fail(c, MFK_ERR_STATE, "no codebook set");
+    CU(c, cudaSetDevice(c->device));
+    // assignment kernel, NCCL sum and read-back queue on the main stream back to back: the host waits once
+    { const int rc = histogram_rows_device(c); if (rc != MFK_OK) return rc; }
+    { const int rc = mfk_allreduce_counts(c, c->bow_counts, (size_t)c->K, nccl_comm); if (rc != MFK_OK) return rc; }
+    return finish_counts(c, counts);      // the overflow flags are this rank's own
 }
 
 int mfk_nccl_unique_id(uint8_t id_out[128]) {

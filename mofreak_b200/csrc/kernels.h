@@ -64,6 +64,8 @@ int launch_set_pairs(cudaStream_t, const int32_t* cur_host, const int32_t* prev_
 void launch_absdiff(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, uint8_t* img);
 void launch_pyramid(cudaStream_t, const Geom&, uint8_t* img);                                  // layers 1..5
 int  score_mask_words(int frame_width);        // 64-bit hit-mask words per (pair, layer row)
+int  score_tile_rows(const int layer_heights[N_LAYERS]);   // tile rows of k_scores over all layers, and the table's capacity
+int  score_tile_rows_max();
 void launch_scores(cudaStream_t, const Geom&, const uint8_t* img, uint8_t* S, unsigned long long* hitmask);
 void launch_row_counts(cudaStream_t, const Geom&, const unsigned long long* hitmask, uint32_t* row_count);
 void launch_fill_candidates(cudaStream_t, const Geom&, const unsigned long long* hitmask, CandBuf);
@@ -84,8 +86,10 @@ void launch_describe(cudaStream_t, const Geom&, const uint8_t* store, int store_
 void launch_mip_only(cudaStream_t, int W, int H, const uint8_t* cur, const uint8_t* prev, const float* kp_xys, int n,
                      uint8_t* motion, uint32_t* err_flag, DeviceTables);
 // --- bag of words --------------------------------------------------------------------------------------
-void launch_bow_assign(cudaStream_t, const uint8_t* desc, size_t stride_bytes, size_t n, const uint8_t* codebook, int K,
-                       int32_t* idx, uint32_t* counts /*nullable*/);
+// returns the launch status (the shared-memory opt-in is per device and is set on every call)
+// n descriptors, or min(n, *d_n) when d_n (a device word) is given
+cudaError_t launch_bow_assign(cudaStream_t, const uint8_t* desc, size_t stride_bytes, size_t n, const uint32_t* d_n /*nullable*/,
+                              const uint8_t* codebook, int K, int32_t* idx, uint32_t* counts /*nullable*/);
 
 // `.mofreak` text (kernels_text.cu): line lengths into len[0..n] (slot n = 0, the scan makes it the total; flags |= 1 if a float
 // needs exponent notation), then the lines at their scanned offsets

@@ -1,9 +1,11 @@
 // Bag-of-words assignment: BagOfWordsRepresentation::bruteForceMatch / hammingDistance, reference
 // src/MoFREAK/BagOfWordsRepresentation.cpp:22-72 — arg-min over the codebook of the 128-bit Hamming
 // distance, lowest index on ties (strict '<', :30) — and the count part of buildHistogram (:107-116).
-// The codebook is staged in shared memory once per block (K x 16 bytes: 9.6 KB for the 600 words of KTH,
-// 158 KB for the 10100 of UCF101); every thread owns one descriptor in registers and streams the codewords
-// as broadcast 128-bit shared loads: 2 XOR + 2 POPC.64 per codeword.  Integer-pipe bound by construction.
+// The codebook is staged in shared memory (K x 16 bytes: 9.6 KB for the 600 words of KTH, 158 KB for the
+// 10100 of UCF101) by ONE bulk copy of the TMA engine per block and chunk (cp.async.bulk, completion on an
+// mbarrier: SASS UBLKCP) — the codebook is a dense, 16-byte aligned array, exactly the 1-D case the engine
+// takes without a tensor map.  Every thread owns one descriptor in registers and streams the codewords as
+// broadcast 128-bit shared loads: 2 XOR + 2 POPC.64 per codeword.  Integer-pipe bound by construction.
 #include "kernels.h"
 
 namespace mfk {
@@ -11,11 +13,51 @@ namespace mfk {
 constexpr int BOW_THREADS = 256;
 constexpr int BOW_SMEM_WORDS_MAX = 13312;      // 208 KB of codewords per pass
 
+namespace {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// one elected thread: arm the barrier with the byte count, then hand the copy to the TMA engine
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+}  // namespace
+
 __global__ void __launch_bounds__(BOW_THREADS)
-k_bow_assign(const uint8_t* __restrict__ desc, size_t stride, size_t n, const uint4* __restrict__ codebook, int K,
-             int32_t* __restrict__ idx, uint32_t* __restrict__ counts) {
-    extern __shared__ uint4 words[];
+k_bow_assign(const uint8_t* __restrict__ desc, size_t stride, size_t n_max, const uint32_t* __restrict__ d_n,
+             const uint4* __restrict__ codebook, int K, int32_t* __restrict__ idx, uint32_t* __restrict__ counts) {
+    extern __shared__ __align__(128) uint4 words[];
+    __shared__ __align__(8) uint64_t bar;
+    const size_t n = d_n ? min(n_max, (size_t)*d_n) : n_max;      // live length on the device (rows accumulated so far)
     const int chunk = min(K, BOW_SMEM_WORDS_MAX);
+    const bool resident = K <= BOW_SMEM_WORDS_MAX;       // the whole codebook fits: staged once per block
+    uint32_t phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        if (resident) bulk_load(words, codebook, (uint32_t)K * 16u, &bar);
+    }
+    __syncthreads();
+    if (resident) { mbar_wait(&bar, phase); phase ^= 1; }
     for (size_t base = (size_t)blockIdx.x * BOW_THREADS; base < n; base += (size_t)gridDim.x * BOW_THREADS) {
         const size_t i = base + threadIdx.x;
         unsigned long long lo = 0, hi = 0;
@@ -28,9 +70,14 @@ k_bow_assign(const uint8_t* __restrict__ desc, size_t stride, size_t n, const ui
         int best = 0x7fffffff, best_k = -1;
         for (int k0 = 0; k0 < K; k0 += chunk) {
             const int kn = min(chunk, K - k0);
-            __syncthreads();
-            for (int k = threadIdx.x; k < kn; k += BOW_THREADS) words[k] = codebook[k0 + k];
-            __syncthreads();
+            if (!resident) {
+                __syncthreads();                             // every thread is done with the previous chunk
+                if (threadIdx.x == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic reads before the engine's writes
+                    bulk_load(words, codebook + k0, (uint32_t)kn * 16u, &bar);
+                }
+                mbar_wait(&bar, phase); phase ^= 1;
+            }
 #pragma unroll 4
             for (int k = 0; k < kn; k++) {
                 const uint4 c = words[k];
@@ -47,19 +94,18 @@ k_bow_assign(const uint8_t* __restrict__ desc, size_t stride, size_t n, const ui
     }
 }
 
-void launch_bow_assign(cudaStream_t st, const uint8_t* desc, size_t stride_bytes, size_t n, const uint8_t* codebook, int K,
-                       int32_t* idx, uint32_t* counts) {
-    if (n == 0 || K <= 0) return;
+cudaError_t launch_bow_assign(cudaStream_t st, const uint8_t* desc, size_t stride_bytes, size_t n, const uint32_t* d_n,
+                              const uint8_t* codebook, int K, int32_t* idx, uint32_t* counts) {
+    if (n == 0 || K <= 0) return cudaSuccess;
     const int chunk = K < BOW_SMEM_WORDS_MAX ? K : BOW_SMEM_WORDS_MAX;
     const size_t smem = (size_t)chunk * 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_bow_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, BOW_SMEM_WORDS_MAX * 16);
-        attr_set = true;
-    }
+    // a per-DEVICE attribute (a process may hold contexts on several GPUs): set it for the current device on every launch
+    cudaError_t e = cudaFuncSetAttribute(k_bow_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, BOW_SMEM_WORDS_MAX * 16);
+    if (e != cudaSuccess) return e;
     size_t blocks = (n + BOW_THREADS - 1) / BOW_THREADS;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_bow_assign<<<(unsigned)blocks, BOW_THREADS, smem, st>>>(desc, stride_bytes, n, reinterpret_cast<const uint4*>(codebook), K, idx, counts);
+    k_bow_assign<<<(unsigned)blocks, BOW_THREADS, smem, st>>>(desc, stride_bytes, n, d_n, reinterpret_cast<const uint4*>(codebook), K, idx, counts);
+    return cudaGetLastError();
 }
 
 }  // namespace mfk

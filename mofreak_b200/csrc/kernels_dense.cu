@@ -343,6 +343,8 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
 }
 
 int score_mask_words(int frame_width) { return (frame_width + SC_TW - 1) / SC_TW; }
+int score_tile_rows(const int lh[N_LAYERS]) { int r = 0; for (int l = 0; l < N_LAYERS; l++) r += (lh[l] + SC_TH - 1) / SC_TH; return r; }
+int score_tile_rows_max() { return (int)(sizeof(ScoreTiles::layer) / sizeof(uint8_t)); }
 
 void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* S, unsigned long long* hitmask) {
     ScoreTiles tiles;

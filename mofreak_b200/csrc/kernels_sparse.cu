@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
         const bool listed = n_pending <= PEND_CAP;      // phase A's list holds them all (order is irrelevant then)
         // candidates are in raster order, so taking the pending ones chunk by chunk keeps every dependency
         // (always raster-earlier) inside the current or an already finished chunk
+        int again;                                      // `more`, read by every thread BEFORE thread 0 may clear it again
         do {
             if (threadIdx.x == 0) { n_list = 0; more = 0; }
             __syncthreads();
@@ -252,8 +253,9 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
             if (threadIdx.x == 0) atomicMax(&cb.counters[6], (uint32_t)rounds);
 #endif
             cursor = next_cursor;
+            again = more;
             __syncthreads();
-        } while (more);
+        } while (again);
         __threadfence();        // seen marks of layer li+1 are complete before its ties are examined
         __syncthreads();
     }

@@ -130,18 +130,23 @@ void MoFREAKUtilities::computeMoFREAKFromFrames(const uint8_t* gray, int width, 
         last_rows_.resize(cap);
         last_text_.resize(cap * 96);
         rc = mfk_extract_clip_text(ctx_, gray, (size_t)width, n_frames, &last_text_[0], last_text_.size(), &n_text, last_rows_.data(), cap, &n);
-        if (rc == MFK_ERR_CAPACITY && (n > cap || n_text > last_text_.size())) {
-            // a buffer of ours was too small; the device kept the accumulation, so read it again with exact sizes
-            last_rows_.resize(n);
-            last_text_.resize(std::max<size_t>(n_text, 1));
-            rc = mfk_rows_text(ctx_, &last_text_[0], last_text_.size(), &n_text);
-            const int rc_rows = mfk_fetch_rows(ctx_, last_rows_.data(), n, &n, nullptr, 0);
-            if (rc == MFK_OK || rc == MFK_ERR_RANGE) { if (rc_rows != MFK_OK) rc = rc_rows; }
-            break;
-        }
-        if (rc == MFK_ERR_CAPACITY && budget_scale_ < 64) {                 // a device-side budget overflowed (very busy frames):
+        if (rc == MFK_ERR_BUDGET && budget_scale_ < 64) {                   // a device-side budget overflowed (very busy frames):
             ensureContext(width, height, budget_scale_ * 4);                // the reference has no such limit, so grow and redo
             continue;
+        }
+        if (rc == MFK_ERR_CAPACITY) {
+            // a buffer of OURS was too small; the device kept the accumulation, so read it again with the sizes it reported
+            last_rows_.resize(std::max<size_t>(n, 1));
+            last_text_.resize(std::max<size_t>(n_text, 1));
+            const size_t want_rows = n;
+            rc = mfk_rows_text(ctx_, &last_text_[0], last_text_.size(), &n_text);
+            const int rc_rows = mfk_fetch_rows(ctx_, last_rows_.data(), last_rows_.size(), &n, nullptr, 0);
+            if (rc == MFK_OK || rc == MFK_ERR_RANGE) { if (rc_rows != MFK_OK) rc = rc_rows; }
+            if (rc == MFK_OK && n != want_rows) {                            // never silently write a short file
+                rc = MFK_ERR_STATE;
+                die("mofreak_b200: the device accumulation changed between the sizing call and the re-read");
+            }
+            break;
         }
         break;
     }

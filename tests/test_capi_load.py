@@ -11,10 +11,13 @@ import mofreak_b200
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_symbols():
-    text = open(os.path.join(ROOT, "include", "mofreak_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(mfk_[a-z0-9_]+)\s*\(", text)))
+def header_symbols(names=("mofreak_b200.h", "mofreak_b200_debug.h")):
+    out = set()
+    for name in names:
+        text = open(os.path.join(ROOT, "include", name)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        out |= set(re.findall(r"\b(mfk_[a-z0-9_]+)\s*\(", text))
+    return sorted(out)
 
 
 def test_library_exports_every_declared_symbol():
@@ -24,6 +27,15 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libmofreak_b200.so does not export %s" % n
     assert sorted(mofreak_b200.SYMBOLS) == names
+
+
+def test_public_header_is_the_drop_in_surface_only():
+    """Debug/profile/synthetic-data instruments live in mofreak_b200_debug.h / mofreak_synth.h, not in the public header."""
+    public = header_symbols(("mofreak_b200.h",))
+    assert not [n for n in public if n.startswith(("mfk_debug_", "mfk_profile_")) or n in ("mfk_set_serial", "mfk_synth_clip")]
+    assert len(public) <= 33
+    synth = ctypes.CDLL(mofreak_b200.capi.SYNTH_LIB_PATH)
+    assert hasattr(synth, "mfk_synth_clip") and not hasattr(mofreak_b200.lib(), "mfk_synth_clip")
 
 
 def test_row_layout_is_32_bytes():

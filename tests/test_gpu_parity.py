@@ -131,7 +131,46 @@ def test_capacity_overflow_is_reported_not_silent():
     with mofreak_b200.Context(320, 240, 16, 2, cand_cap_per_pair=64, row_cap_per_pair=8) as ctx:
         with pytest.raises(mofreak_b200.MofreakError) as e:
             ctx.extract_clip(clip)
-        assert e.value.code == mofreak_b200.capi.MFK_ERR_CAPACITY
+        assert e.value.code == mofreak_b200.capi.MFK_ERR_BUDGET
+
+
+def test_small_caller_buffers_and_budget_overflow_are_told_apart(orc):
+    """MFK_ERR_CAPACITY = the caller's buffer is too small: sizes are reported and the accumulation is kept, so a re-read
+    with larger buffers gives the full result.  MFK_ERR_BUDGET = a device budget overflowed: no sizes, nothing to re-read."""
+    import ctypes as C
+    clip = mofreak_b200.synth_clip(320, 240, 9, 72)
+    want = orc.extract_clip(clip)
+    assert len(want) > 50
+    L = mofreak_b200.lib()
+    with mofreak_b200.Context(320, 240, 16, 4) as ctx:
+        rows = np.empty(8, mofreak_b200.ROW_DTYPE)
+        text = np.empty(64, np.uint8)
+        n, nb = C.c_size_t(), C.c_size_t()
+        rc = L.mfk_extract_clip_text(ctx._h, clip.ctypes.data_as(C.c_void_p), 320, 9, text.ctypes.data_as(C.c_void_p), text.size, C.byref(nb),
+                                     rows.ctypes.data_as(C.c_void_p), rows.size, C.byref(n))
+        assert rc == mofreak_b200.capi.MFK_ERR_CAPACITY and n.value == len(want) and nb.value > 64
+        text_full = ctx.rows_text()
+        got, _ = ctx.fetch_rows(n.value)
+        assert util.rows_equal(got, want)
+        assert text_full == orc.format_mofreak(want) and len(text_full) == nb.value
+    with mofreak_b200.Context(320, 240, 16, 4, cand_cap_per_pair=64, row_cap_per_pair=8) as ctx:
+        rows = np.empty(100000, mofreak_b200.ROW_DTYPE)
+        text = np.empty(1 << 22, np.uint8)
+        n, nb = C.c_size_t(7), C.c_size_t(7)
+        rc = L.mfk_extract_clip_text(ctx._h, clip.ctypes.data_as(C.c_void_p), 320, 9, text.ctypes.data_as(C.c_void_p), text.size, C.byref(nb),
+                                     rows.ctypes.data_as(C.c_void_p), rows.size, C.byref(n))
+        assert rc == mofreak_b200.capi.MFK_ERR_BUDGET and n.value == 0 and nb.value == 0
+
+
+def test_negative_slots_are_rejected():
+    with mofreak_b200.Context(160, 120, 16, 4) as ctx:
+        ctx.upload_frames(mofreak_b200.synth_clip(160, 120, 8, 3), 0)
+        with pytest.raises(mofreak_b200.MofreakError) as e:
+            ctx.extract_pairs(np.array([5, -1], np.int32), np.array([0, 1], np.int32), np.array([4, 5], np.int32))
+        assert e.value.code == mofreak_b200.capi.MFK_ERR_ARG
+        ctx.extract_pairs(np.array([5], np.int32), np.array([0], np.int32), np.array([4], np.int32))     # the context still works
+        rows, _ = ctx.fetch_rows(10000)
+        assert len(rows) >= 0
 
 
 def test_mip_facade(orc):
