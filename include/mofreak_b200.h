@@ -172,11 +172,15 @@ int  mfk_bow_histogram(mfk_ctx* ctx, const uint8_t* desc, size_t N, uint32_t* co
  * over all ranks of `nccl_comm` (an ncclComm_t) on the context's stream.  Async.  Returns
  * MFK_ERR_STATE when the library was built without NCCL.  No counterpart in the reference. */
 int  mfk_allreduce_counts(mfk_ctx* ctx, uint32_t* d_counts, size_t n, void* nccl_comm);
-/* mfk_bow_histogram_rows for a video whose rows are spread over the ranks of `nccl_comm`: every rank assigns its own
- * accumulated rows, the count vectors are summed over the ranks (ncclAllReduce, uint32 sum, NVLink/NVSwitch) and every
- * rank receives the video's total counts[K] (HOST).  Assignment kernel, collective and read-back are queued back to
- * back on the context's stream; the host waits once.  Collective: every rank of the communicator must call it. */
-int  mfk_bow_histogram_rows_reduced(mfk_ctx* ctx, uint32_t* counts, void* nccl_comm);
+/* One word-count vector per VIDEO from the rows accumulated on the device - what the reference computes per `.mofreak`
+ * file (BagOfWordsRepresentation::buildHistogram, :74-138, called once per file from convertFileToBOWFeature :960-1031).
+ * The pairs queued since the last reset are split into n_videos consecutive groups of pairs_per_video[v] pairs
+ * (NULL with n_videos == 1: all of them); counts = n_videos x K HOST uint32, overwritten.
+ * nccl_comm != NULL: the videos' frame ranges are sharded over the ranks of that communicator (every rank queued ITS
+ * frames of the same n_videos videos); the count vectors are summed over the ranks (ncclAllReduce, uint32 sum, over
+ * NVLink/NVSwitch) and every rank receives the totals.  Collective then: every rank must call it.  Assignment kernel,
+ * collective and read-back are queued back to back on the context's stream; the host waits once. */
+int  mfk_bow_histogram_videos(mfk_ctx* ctx, const uint32_t* pairs_per_video, int n_videos, uint32_t* counts, void* nccl_comm);
 
 /* Helpers to build the communicator for mfk_allreduce_counts without linking NCCL (same run-time resolution): rank 0 calls
  * mfk_nccl_unique_id and ships the 128 bytes to the other ranks by any means (torch.distributed, MPI, a file); every rank

@@ -26,7 +26,7 @@ SYNTH_LIB_PATH = os.path.join(HERE, "synth", "libmofreak_synth.so")
 SYMBOLS = [
     "mfk_create", "mfk_create_ex", "mfk_destroy", "mfk_last_error", "mfk_sync", "mfk_host_alloc", "mfk_host_free", "mfk_upload_frames", "mfk_upload_frames_bgr", "mfk_frame_store",
     "mfk_extract_pairs", "mfk_fetch_rows", "mfk_rows_device", "mfk_reset_rows", "mfk_extract_clip", "mfk_rows_text", "mfk_format_rows", "mfk_extract_clip_text", "mfk_mip_describe",
-    "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram", "mfk_bow_histogram_rows_reduced",
+    "mfk_bow_set_codebook", "mfk_bow_assign", "mfk_bow_assign_device", "mfk_bow_histogram_rows", "mfk_bow_histogram", "mfk_bow_histogram_videos",
     "mfk_allreduce_counts", "mfk_nccl_unique_id", "mfk_nccl_comm_init", "mfk_nccl_comm_destroy", "mfk_timer_start", "mfk_timer_stop", "mfk_profile_enable", "mfk_profile_read", "mfk_profile_timeline",
     "mfk_set_serial", "mfk_launch_count", "mfk_debug_layer", "mfk_debug_keypoints", "mfk_debug_counters", "mfk_freak_scale_index", "mfk_version",
 ]
@@ -84,7 +84,7 @@ def lib():
     L.mfk_bow_assign_device.argtypes = [p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.mfk_bow_histogram_rows.argtypes = [p, u32p]
     L.mfk_bow_histogram.argtypes = [p, u8p, C.c_size_t, u32p]
-    L.mfk_bow_histogram_rows_reduced.argtypes = [p, u32p, C.c_void_p]
+    L.mfk_bow_histogram_videos.argtypes = [p, u32p, C.c_int, u32p, C.c_void_p]
     L.mfk_allreduce_counts.argtypes = [p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.mfk_nccl_unique_id.argtypes = [C.c_void_p]
     L.mfk_nccl_comm_init.argtypes = [p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
@@ -314,10 +314,15 @@ class Context:
         self._check(self._L.mfk_bow_histogram_rows(self._h, _ptr(counts)))
         return counts
 
-    def bow_histogram_rows_reduced(self, comm):
-        """Counts of this rank's accumulated rows summed over all ranks of `comm` (collective)."""
-        counts = np.zeros(self.K, np.uint32)
-        self._check(self._L.mfk_bow_histogram_rows_reduced(self._h, _ptr(counts), comm))
+    def bow_histogram_videos(self, pairs_per_video=None, comm=None):
+        """[n_videos, K] word counts of the accumulated rows, one vector per group of consecutive queued pairs; with `comm`
+        the vectors are summed over the ranks (collective)."""
+        if pairs_per_video is None:
+            ppv, n = None, 1
+        else:
+            ppv = np.ascontiguousarray(pairs_per_video, np.uint32); n = ppv.size
+        counts = np.zeros((n, self.K), np.uint32)
+        self._check(self._L.mfk_bow_histogram_videos(self._h, _ptr(ppv) if ppv is not None else None, n, _ptr(counts), comm))
         return counts
 
     # --- multi-GPU exchange of word counts ---

@@ -926,14 +926,47 @@ int mfk_allreduce_counts(mfk_ctx* c, uint32_t* d_counts, size_t n, void* nccl_co
     return MFK_OK;
 }
 
-int mfk_bow_histogram_rows_reduced(mfk_ctx* c, uint32_t* counts, void* nccl_comm) {
-    if (!c || !counts || !nccl_comm) return fail(c, MFK_ERR_ARG, "bad argument to mfk_bow_histogram_rows_reduced");
+int mfk_bow_histogram_videos(mfk_ctx* c, const uint32_t* pairs_per_video, int n_videos, uint32_t* counts, void* nccl_comm) {
+    if (!c || !counts || n_videos < 1) return fail(c, MFK_ERR_ARG, "bad argument to mfk_bow_histogram_videos");
     if (!c->codebook) return fail(c, MFK_ERR_STATE, "no codebook set");
     CU(c, cudaSetDevice(c->device));
-    // assignment kernel, NCCL sum and read-back queue on the main stream back to back: the host waits once
-    { const int rc = histogram_rows_device(c); if (rc != MFK_OK) return rc; }
-    { const int rc = mfk_allreduce_counts(c, c->bow_counts, (size_t)c->K, nccl_comm); if (rc != MFK_OK) return rc; }
-    return finish_counts(c, counts);      // the overflow flags are this rank's own
+    if (!pairs_per_video && n_videos != 1) return fail(c, MFK_ERR_ARG, "pairs_per_video is required for more than one video");
+    std::vector<uint32_t> start((size_t)n_videos + 1, 0);
+    if (pairs_per_video) for (int v = 0; v < n_videos; v++) start[v + 1] = start[v] + pairs_per_video[v];
+    else start[1] = (uint32_t)c->pairs_queued;
+    if (start[n_videos] != c->pairs_queued)
+        return fail(c, MFK_ERR_ARG, "pairs_per_video sums to %u, but %zu pairs were queued since the last reset", start[n_videos], c->pairs_queued);
+    const size_t cells = (size_t)n_videos * c->K;
+    if (cells > (size_t)c->bow_counts_cap) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->bow_counts); c->bow_counts = nullptr; c->bow_counts_cap = 0;
+        CU(c, dalloc(&c->bow_counts, cells));
+        c->bow_counts_cap = (int)cells;
+    }
+    // scratch: pair_start [n+1] | row offsets [n+2] | scan scratch
+    const size_t nv1 = (size_t)n_videos + 1;
+    { const int rc = ensure_bow_tmp(c, (2 * nv1 + 1 + nv1 / 2048 + 8) * sizeof(uint32_t)); if (rc != MFK_OK) return rc; }
+    uint32_t* d_start = (uint32_t*)c->bow_tmp;
+    uint32_t* d_off = d_start + nv1;
+    uint32_t* d_scratch = d_off + nv1 + 1;
+    { const int rc = settle(c); if (rc != MFK_OK) return rc; }
+    // pageable source: the runtime stages it before returning, so `start` may go out of scope
+    CU(c, cudaMemcpyAsync(d_start, start.data(), nv1 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemsetAsync(c->bow_counts, 0, cells * 4, c->stream));
+    { Span s(c, P_BOW, 5);
+      launch_video_rows(c->stream, c->pair_rows, d_start, n_videos, d_off);
+      launch_exclusive_scan(c->stream, d_off, n_videos, nullptr, d_scratch);
+      // descriptor = appearance | motion = bytes 16..31 of each 32-byte row; the live row count is read on the device
+      CU(c, launch_bow_assign(c->stream, (const uint8_t*)c->rows_buf + 16, 32, c->row_cap, c->counters + 1, c->codebook, c->K, nullptr,
+                              c->bow_counts, d_off, n_videos)); }
+    if (nccl_comm) { const int rc = mfk_allreduce_counts(c, c->bow_counts, cells, nccl_comm); if (rc != MFK_OK) return rc; }
+    uint32_t h[4] = {0, 0, 0, 0};
+    CU(c, cudaMemcpyAsync(counts, c->bow_counts, cells * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(h, c->counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (h[0]) return fail(c, MFK_ERR_BUDGET, "budget overflow (%s%s); recreate the context with larger budgets (mfk_create_ex)",
+                          (h[0] & 1) ? "candidates " : "", (h[0] & 2) ? "rows" : "");      // this rank's own flags
+    return MFK_OK;
 }
 
 int mfk_nccl_unique_id(uint8_t id_out[128]) {

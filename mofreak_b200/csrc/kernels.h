@@ -87,9 +87,12 @@ void launch_mip_only(cudaStream_t, int W, int H, const uint8_t* cur, const uint8
                      uint8_t* motion, uint32_t* err_flag, DeviceTables);
 // --- bag of words --------------------------------------------------------------------------------------
 // returns the launch status (the shared-memory opt-in is per device and is set on every call)
-// n descriptors, or min(n, *d_n) when d_n (a device word) is given
+// n descriptors, or min(n, *d_n) when d_n (a device word) is given.  With seg_off (n_seg + 1 ascending row offsets) the
+// counts are per segment: counts[seg * K + word]
 cudaError_t launch_bow_assign(cudaStream_t, const uint8_t* desc, size_t stride_bytes, size_t n, const uint32_t* d_n /*nullable*/,
-                              const uint8_t* codebook, int K, int32_t* idx, uint32_t* counts /*nullable*/);
+                              const uint8_t* codebook, int K, int32_t* idx, uint32_t* counts /*nullable*/,
+                              const uint32_t* seg_off = nullptr, int n_seg = 0);
+void launch_video_rows(cudaStream_t, const uint32_t* pair_rows, const uint32_t* pair_start, int n_videos, uint32_t* out);
 
 // `.mofreak` text (kernels_text.cu): line lengths into len[0..n] (slot n = 0, the scan makes it the total; flags |= 1 if a float
 // needs exponent notation), then the lines at their scanned offsets

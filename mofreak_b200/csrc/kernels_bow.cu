@@ -45,7 +45,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(BOW_THREADS)
 k_bow_assign(const uint8_t* __restrict__ desc, size_t stride, size_t n_max, const uint32_t* __restrict__ d_n,
-             const uint4* __restrict__ codebook, int K, int32_t* __restrict__ idx, uint32_t* __restrict__ counts) {
+             const uint4* __restrict__ codebook, int K, int32_t* __restrict__ idx, uint32_t* __restrict__ counts,
+             const uint32_t* __restrict__ seg_off, int n_seg) {
     extern __shared__ __align__(128) uint4 words[];
     __shared__ __align__(8) uint64_t bar;
     const size_t n = d_n ? min(n_max, (size_t)*d_n) : n_max;      // live length on the device (rows accumulated so far)
@@ -89,13 +90,21 @@ k_bow_assign(const uint8_t* __restrict__ desc, size_t stride, size_t n_max, cons
         }
         if (i < n) {
             if (idx) idx[i] = best_k;
-            if (counts && best_k >= 0) atomicAdd(&counts[best_k], 1u);
+            if (counts && best_k >= 0) {
+                size_t at = (size_t)best_k;
+                if (seg_off) {                               // the video this row belongs to: last v with seg_off[v] <= i
+                    int lo_v = 0, hi_v = n_seg;              // seg_off[n_seg] = total rows > i
+                    while (hi_v - lo_v > 1) { const int mid = (lo_v + hi_v) >> 1; if (seg_off[mid] <= (uint32_t)i) lo_v = mid; else hi_v = mid; }
+                    at += (size_t)lo_v * K;
+                }
+                atomicAdd(&counts[at], 1u);
+            }
         }
     }
 }
 
 cudaError_t launch_bow_assign(cudaStream_t st, const uint8_t* desc, size_t stride_bytes, size_t n, const uint32_t* d_n,
-                              const uint8_t* codebook, int K, int32_t* idx, uint32_t* counts) {
+                              const uint8_t* codebook, int K, int32_t* idx, uint32_t* counts, const uint32_t* seg_off, int n_seg) {
     if (n == 0 || K <= 0) return cudaSuccess;
     const int chunk = K < BOW_SMEM_WORDS_MAX ? K : BOW_SMEM_WORDS_MAX;
     const size_t smem = (size_t)chunk * 16;
@@ -104,8 +113,24 @@ cudaError_t launch_bow_assign(cudaStream_t st, const uint8_t* desc, size_t strid
     if (e != cudaSuccess) return e;
     size_t blocks = (n + BOW_THREADS - 1) / BOW_THREADS;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_bow_assign<<<(unsigned)blocks, BOW_THREADS, smem, st>>>(desc, stride_bytes, n, d_n, reinterpret_cast<const uint4*>(codebook), K, idx, counts);
+    k_bow_assign<<<(unsigned)blocks, BOW_THREADS, smem, st>>>(desc, stride_bytes, n, d_n, reinterpret_cast<const uint4*>(codebook), K, idx, counts,
+                                                                  seg_off, n_seg);
     return cudaGetLastError();
+}
+
+// rows per video from the per-pair row counts: video v owns the queued pairs [pair_start[v], pair_start[v+1]); slot n_videos = 0
+// (the exclusive scan that follows turns the array into row offsets, slot n_videos = total)
+__global__ void k_video_rows(const uint32_t* __restrict__ pair_rows, const uint32_t* __restrict__ pair_start, int n_videos,
+                             uint32_t* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > n_videos) return;
+    uint32_t sum = 0;
+    if (v < n_videos) for (uint32_t p = pair_start[v]; p < pair_start[v + 1]; p++) sum += pair_rows[p];
+    out[v] = sum;
+}
+
+void launch_video_rows(cudaStream_t st, const uint32_t* pair_rows, const uint32_t* pair_start, int n_videos, uint32_t* out) {
+    k_video_rows<<<(n_videos + 1 + 127) / 128, 128, 0, st>>>(pair_rows, pair_start, n_videos, out);
 }
 
 }  // namespace mfk

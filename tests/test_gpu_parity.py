@@ -152,7 +152,7 @@ def test_small_caller_buffers_and_budget_overflow_are_told_apart(orc):
         text_full = ctx.rows_text()
         got, _ = ctx.fetch_rows(n.value)
         assert util.rows_equal(got, want)
-        assert text_full == orc.format_mofreak(want) and len(text_full) == nb.value
+        assert text_full.decode() == orc.format_mofreak(want) and len(text_full) == nb.value
     with mofreak_b200.Context(320, 240, 16, 4, cand_cap_per_pair=64, row_cap_per_pair=8) as ctx:
         rows = np.empty(100000, mofreak_b200.ROW_DTYPE)
         text = np.empty(1 << 22, np.uint8)
