@@ -383,17 +383,20 @@ def run_ours(args, name, cfg):
     # overlaps the uploads and kernels of the other.
     row_cap = int(n_rows_step * 1.5) + 65536
     if streams_mode:
-        # every context owns half of the streams as frame RINGS of 2 x P slots per stream: a step writes the stream's P new
-        # frames into the half the previous step did not use; the 5 frames of look-back are still there - nothing is
-        # uploaded twice.  One bench step = one half-step on each context.
-        halves = [list(range(0, V // 2)), list(range(V // 2, V))] if V >= 2 else [list(range(V)), []]
-        ring = 2 * P
+        # The streams form two groups, one per context; a bench step advances ONE group by SEGS x P frames (= the step's
+        # V x P processed frames) and the groups alternate, so that the blocking row fetch of one group overlaps the uploads
+        # and kernels of the other.  Every stream is a frame RING of 2 x SEGS segments of P slots on the device: a turn writes
+        # the stream's new frames into the segments the previous turn did not use; the 5 frames of look-back are still
+        # there - nothing is uploaded twice.
+        groups = [list(range(0, V // 2)), list(range(V // 2, V))] if V >= 2 and V % 2 == 0 else [list(range(V))]
+        SEGS = len(groups)                  # segments of P frames a turn appends to each stream of its group
+        ring = 2 * SEGS * P
         chunk_v = max(1, MAX_PAIRS // P)
         e2e_ctx = []
-        for vids in halves:
-            c = mofreak_b200.Context(W, H, max(len(vids), 1) * ring, MAX_PAIRS, device=local_rank)
+        for vids in groups:
+            c = mofreak_b200.Context(W, H, len(vids) * ring, MAX_PAIRS, device=local_rank)
             rows_host = torch.empty((row_cap, 32), dtype=torch.uint8, pin_memory=True)
-            # initial look-back f0..f4 at the end of half 1 (what a forward segment in half 0 looks back to)
+            # initial look-back f0..f4 at the end of the ring (what the first forward segment looks back to)
             for j, v in enumerate(vids):
                 c.upload_raw(host.ptr + v * HPV * frame_bytes, GAP, j * ring + ring - GAP)
             c.sync()
@@ -407,25 +410,26 @@ def run_ours(args, name, cfg):
         i_in = np.arange(P)
 
         def submit(e):
-            c, k = e["ctx"], e["seg"]
-            half = k % 2
-            src_off = (GAP if half == 0 else FPV) * frame_bytes          # forward segment F / backward segment B
+            c = e["ctx"]
             c.reset_rows()
-            j0 = 0
-            for n_s in e["sizes"]:
-                cu, pr, lb = [], [], []
-                for j in range(j0, j0 + n_s):
-                    v = e["vids"][j]
-                    base = j * ring
-                    c.upload_raw(host.ptr + v * HPV * frame_bytes + src_off, P, base + half * P)
-                    cu.append(base + half * P + i_in)
-                    pr.append(np.where(i_in >= GAP, base + half * P + i_in - GAP, base + (1 - half) * P + P - GAP + i_in))
-                    lb.append(k * P + i_in + GAP - 1)
-                c.extract_pairs(np.concatenate(cu), np.concatenate(pr), np.concatenate(lb))
-                j0 += n_s
-            e["seg"] = k + 1
+            for _ in range(SEGS):
+                k = e["seg"]
+                q = k % (2 * SEGS)                                         # ring segment this pass writes
+                src_off = (GAP if k % 2 == 0 else FPV) * frame_bytes       # forward segment F / backward segment B
+                j0 = 0
+                for n_s in e["sizes"]:
+                    cu, pr, lb = [], [], []
+                    for j in range(j0, j0 + n_s):
+                        v = e["vids"][j]
+                        base = j * ring
+                        c.upload_raw(host.ptr + v * HPV * frame_bytes + src_off, P, base + q * P)
+                        cu.append(base + q * P + i_in)
+                        pr.append(base + (q * P + i_in - GAP) % ring)      # 5 frames earlier in the ring
+                        lb.append(k * P + i_in + GAP - 1)
+                    c.extract_pairs(np.concatenate(cu), np.concatenate(pr), np.concatenate(lb))
+                    j0 += n_s
+                e["seg"] = k + 1
         h2d_per_step = V * P * frame_bytes
-        parts_per_step = [e for e in e2e_ctx if e["vids"]]
     else:
         # clips: whole steps alternate between two contexts; a step uploads every frame of every clip
         chunk_v = max(1, MAX_PAIRS // P)
@@ -445,7 +449,6 @@ def run_ours(args, name, cfg):
                 ps = slice(v0 * P, v1 * P)
                 c.extract_pairs(cur[ps], prev[ps], label[ps])
         h2d_per_step = n_frames * frame_bytes
-        parts_per_step = None
 
     def collect(e):
         if cfg["bow"]:
@@ -456,11 +459,11 @@ def run_ours(args, name, cfg):
         """Returns the average number of rows fetched per step."""
         pending, acc = None, 0
         for k in range(steps):
-            for e in (parts_per_step if streams_mode else [e2e_ctx[k % 2]]):
-                submit(e)
-                if pending is not None:
-                    acc += collect(pending)
-                pending = e
+            e = e2e_ctx[k % len(e2e_ctx)]
+            submit(e)
+            if pending is not None:
+                acc += collect(pending)
+            pending = e
         if pending is not None:
             acc += collect(pending)
         return acc / max(1, steps)
@@ -522,8 +525,9 @@ def run_ours(args, name, cfg):
                     "h2d_gb_per_s_per_gpu": h2d_per_step / (ms_e2e / args.steps * 1e-3) / 1e9,
                     "h2d_ceiling_gb_per_s_per_gpu": ((ceiling or {}).get(str(world)) or {}).get("gb_per_s_per_gpu_min"),
                     "h2d_ceiling_source": "profiles/h2d_ceiling.json (copies only, same buffers and chunk sizes, %d ranks)" % world if ceiling else None,
-                    "frames": ("continuous streams: every step uploads the %d NEW frames of each stream into a device frame ring; the "
-                               "5-frame look-back stays resident" % P) if streams_mode else "clips: every step uploads every frame of every clip",
+                    "frames": ("continuous streams in two groups of %d, one group per context: a step advances one group by %d new frames per "
+                               "stream (= %d processed frames), written into device frame rings; the 5-frame look-back stays resident, "
+                               "nothing is uploaded twice" % (V // 2, 2 * P, V * P)) if streams_mode else "clips: every step uploads every frame of every clip",
                     "timing": "host clock around the K steps, device synchronised on both sides (every fetch blocks, so "
                               "this bounds the device time from above); two contexts take turns so that the row fetch of one "
                               "overlaps the uploads and kernels of the other"},

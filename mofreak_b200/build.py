@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmofreak_b200.so")
 
-CU_SOURCES = ["context.cu", "kernels_dense.cu", "kernels_sparse.cu", "kernels_desc.cu", "kernels_bow.cu", "kernels_text.cu"]
+CU_SOURCES = ["context.cu", "kernels_front.cu", "kernels_dense.cu", "kernels_sparse.cu", "kernels_desc.cu", "kernels_bow.cu", "kernels_text.cu"]
 CPP_SOURCES = [os.path.join(CSRC, "tables.cpp")]
 SYNTH_SRC = os.path.join(HERE, "synth", "synth.cpp")
 SYNTH_LIB = os.path.join(HERE, "synth", "libmofreak_synth.so")      # plain C++, no CUDA: frames for tests/bench

@@ -31,9 +31,9 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum ProfId { P_ABSDIFF, P_PYRAMID, P_SCORES, P_SCAN, P_FILL, P_INTEGRAL, P_PHASE_A, P_PHASE_B, P_COMPACT, P_DESCRIBE,
+enum ProfId { P_FRONT, P_ABSDIFF, P_PYRAMID, P_SCORES, P_SCAN, P_FILL, P_INTEGRAL, P_PHASE_A, P_PHASE_B, P_COMPACT, P_DESCRIBE,
               P_BOW, P_MIP, P_TEXT, P_COUNT };
-const char* const kProfNames[P_COUNT] = {"absdiff", "pyramid", "scores", "scan", "fill_candidates", "integral", "phase_a",
+const char* const kProfNames[P_COUNT] = {"front", "absdiff", "pyramid", "scores", "scan", "fill_candidates", "integral", "phase_a",
                                          "phase_b", "compact", "describe", "bow_assign", "mip_only", "text"};
 // kernels launched per call of each launcher family (for gpu_launches accounting)
 struct ProfSpan { int id; cudaEvent_t a, b; };
@@ -50,7 +50,14 @@ struct mfk_ctx {
     cudaEvent_t upload_done = nullptr;
     bool upload_pending = false;
     enum { MAX_LANES = 4 };
-    struct ReadRec { int lo = 0, hi = -1; cudaEvent_t ev[MAX_LANES] = {}; bool on[MAX_LANES] = {}; bool valid = false; };
+    // slots a queued launch sequence still reads, as a few [lo, hi] intervals (frame rings: one interval per stream), so that
+    // an upload only waits for the kernels that really read the slots it overwrites
+    struct ReadRec {
+        enum { MAX_IV = 16 };
+        int lo[MAX_IV], hi[MAX_IV], n_iv = 0;
+        cudaEvent_t ev[MAX_LANES] = {}; bool on[MAX_LANES] = {}; bool valid = false;
+        bool overlaps(int a, int b) const { for (int i = 0; i < n_iv; i++) if (lo[i] <= b && hi[i] >= a) return true; return false; }
+    };
     ReadRec readers[8];                   // which slot ranges recent launch sequences still read
     int reader_next = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -80,6 +87,7 @@ struct mfk_ctx {
     bool reset_pending = false;           // mfk_reset_rows is applied in-line by the next launch sequence (or by settle())
     bool main_wait_pending = false;       // the next launch sequence orders its shared-row part after main_mark
     bool serial = false;
+    bool fused_front = true;              // MFK_FUSED_FRONT=0 forces the separate dense kernels (A/B measurements, wide frames use them anyway)
     uint64_t batches = 0;
     int last_lane = 0;
     uint32_t* counters = nullptr;
@@ -268,17 +276,20 @@ int run_batch(mfk_ctx* c, const int32_t* cur, const int32_t* prev, const int32_t
     else { CU(c, cudaMemsetAsync(L.maps.seen, 0, (size_t)c->max_pairs * c->pyr_px, st)); L.seen_F = F; }
     CU(c, cudaMemsetAsync(L.cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(L.cb.q_count, 0, 4 * sizeof(uint32_t), st));
-    { Span s(c, P_ABSDIFF, 1, st);   launch_absdiff(st, g, c->store, c->store_frames, pl, L.maps.img); }
+    // dense front: one fused kernel (difference, pyramid, row sums) for frames up to 2048 wide, the separate kernels beyond
+    const bool fused = c->fused_front && front_supported(g);
+    if (fused) { Span s(c, P_FRONT, 1, st); CU(c, launch_front(st, g, c->store, c->store_frames, pl, L.maps.img, L.integral_left)); }
+    else { Span s(c, P_ABSDIFF, 1, st);   launch_absdiff(st, g, c->store, c->store_frames, pl, L.maps.img); }
     // the integral image only needs layer 0: fork it onto the side stream, join before the descriptor kernel
     if (c->serial) {
-        Span s(c, P_INTEGRAL, 2, st);  launch_integral(st, g, L.maps.img, L.integral, L.integral_left);
+        Span s(c, P_INTEGRAL, fused ? 1 : 2, st);  launch_integral(st, g, L.maps.img, L.integral, L.integral_left, fused);
     } else {
         CU(c, cudaEventRecord(L.aux_fork, st));
         CU(c, cudaStreamWaitEvent(L.aux_stream, L.aux_fork, 0));
-        { Span s(c, P_INTEGRAL, 2, L.aux_stream);  launch_integral(L.aux_stream, g, L.maps.img, L.integral, L.integral_left); }
+        { Span s(c, P_INTEGRAL, fused ? 1 : 2, L.aux_stream);  launch_integral(L.aux_stream, g, L.maps.img, L.integral, L.integral_left, fused); }
         CU(c, cudaEventRecord(L.aux_join, L.aux_stream));
     }
-    { Span s(c, P_PYRAMID, 5, st);   launch_pyramid(st, g, L.maps.img); }
+    if (!fused) { Span s(c, P_PYRAMID, 5, st);   launch_pyramid(st, g, L.maps.img); }
     { Span s(c, P_SCORES, 1, st);    launch_scores(st, g, L.maps.img, L.maps.S, L.hitmask); }
     { Span s(c, P_SCAN, 4, st);      launch_row_counts(st, g, L.hitmask, L.cb.row_count);
                                      launch_exclusive_scan(st, L.cb.row_count, F * g.rows, nullptr, L.scan_scratch); }
@@ -439,6 +450,7 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     // tuning knob (documented in the header at mfk_create): number of buffer sets, 1..4
     if (const char* e = getenv("MFK_LANES")) c->lanes_built = std::max(1, std::min((int)mfk_ctx::MAX_LANES, atoi(e)));
     c->n_lanes = c->lanes_built;
+    if (const char* e = getenv("MFK_FUSED_FRONT")) c->fused_front = atoi(e) != 0;
     for (int li = 0; li < c->lanes_built; li++) {
         mfk_ctx::Lane& L = c->lane[li];
         CUC(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
@@ -545,7 +557,7 @@ int mfk_upload_frames(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_fram
         const int run = std::min(n_frames - done, c->store_frames - slot);     // contiguous slots before the wrap
         // slots still being read by queued launch sequences must not be overwritten under them
         for (auto& r : c->readers)
-            if (r.valid && r.lo <= slot + run - 1 && r.hi >= slot)
+            if (r.valid && r.overlaps(slot, slot + run - 1))
                 for (int k = 0; k < mfk_ctx::MAX_LANES; k++) if (r.on[k]) CU(c, cudaStreamWaitEvent(c->copy_stream, r.ev[k], 0));
         const uint8_t* src = gray + (size_t)done * stride * c->H;
         if (stride == (size_t)c->W)
@@ -579,7 +591,7 @@ int mfk_upload_frames_bgr(mfk_ctx* c, const uint8_t* bgr, size_t stride, int n_f
         const int slot = (slot0 + done) % c->store_frames;
         const int run = std::min(std::min(n_frames - done, c->store_frames - slot), chunk);
         for (auto& r : c->readers)
-            if (r.valid && r.lo <= slot + run - 1 && r.hi >= slot)
+            if (r.valid && r.overlaps(slot, slot + run - 1))
                 for (int k = 0; k < mfk_ctx::MAX_LANES; k++) if (r.on[k]) CU(c, cudaStreamWaitEvent(c->copy_stream, r.ev[k], 0));
         const uint8_t* src = bgr + (size_t)done * stride * c->H;
         // the staging buffer is reused in stream order: the previous round's conversion kernel runs before this copy
@@ -630,17 +642,29 @@ int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_s
         if (rc != MFK_OK) return rc;
     }
     c->pairs_queued += (size_t)n_pairs;
-    // remember which slots this call reads until its kernels have run (conservative [min, max] range)
-    int lo = c->store_frames, hi = -1;
-    for (int i = 0; i < n_pairs; i++) {
-        const int a = cur_slot[i] % c->store_frames, b = prev_slot[i] % c->store_frames;
-        lo = std::min(lo, std::min(a, b)); hi = std::max(hi, std::max(a, b));
+    // remember which slots this call reads until its kernels have run: the distinct slots as maximal runs of consecutive
+    // slots; more runs than a record holds collapse into one conservative [min, max] range
+    std::vector<int> slots;
+    slots.reserve(2 * (size_t)n_pairs);
+    for (int i = 0; i < n_pairs; i++) { slots.push_back(cur_slot[i] % c->store_frames); slots.push_back(prev_slot[i] % c->store_frames); }
+    std::sort(slots.begin(), slots.end());
+    slots.erase(std::unique(slots.begin(), slots.end()), slots.end());
+    int iv_lo[mfk_ctx::ReadRec::MAX_IV], iv_hi[mfk_ctx::ReadRec::MAX_IV], n_iv = 0;
+    bool too_many = false;
+    for (size_t i = 0; i < slots.size();) {
+        size_t j = i;
+        while (j + 1 < slots.size() && slots[j + 1] == slots[j] + 1) j++;
+        if (n_iv == mfk_ctx::ReadRec::MAX_IV) { too_many = true; break; }
+        iv_lo[n_iv] = slots[i]; iv_hi[n_iv] = slots[j]; n_iv++;
+        i = j + 1;
     }
+    if (too_many) { iv_lo[0] = slots.front(); iv_hi[0] = slots.back(); n_iv = 1; }
     mfk_ctx::ReadRec& rec = c->readers[c->reader_next];
     c->reader_next = (c->reader_next + 1) % 8;
     if (rec.valid)          // recycled record: keep its ordering
         for (int k = 0; k < mfk_ctx::MAX_LANES; k++) if (rec.on[k]) CU(c, cudaStreamWaitEvent(c->copy_stream, rec.ev[k], 0));
-    rec.lo = lo; rec.hi = hi; rec.valid = true;
+    rec.n_iv = n_iv; rec.valid = true;
+    for (int i = 0; i < n_iv; i++) { rec.lo[i] = iv_lo[i]; rec.hi[i] = iv_hi[i]; }
     for (int k = 0; k < mfk_ctx::MAX_LANES; k++) {
         rec.on[k] = touched[k];
         if (touched[k]) CU(c, cudaEventRecord(rec.ev[k], c->lane[k].stream));

@@ -10,9 +10,10 @@ __device__ __forceinline__ int avg_up(int a, int b) { return (a + b + 1) >> 1; }
 // brisk.cpp:1840-1972: paired 16-byte blocks use avg-of-avg (both rounding up); an odd trailing block a
 // truncating pair mean of the vertical averages (:1917-1942); the (cols % 16) / 2 leftover outputs a 4-tap
 // truncating mean over columns k, k+1 counted from the end of the blocks (:1958-1964).
-__device__ __forceinline__ int half_px(const uint8_t* __restrict__ src, int w, int ox, int oy) {
-    const uint8_t* up = src + (2 * oy) * w;
-    const uint8_t* lo = up + w;
+// src: rows of `pitch` bytes, `w` of them image columns
+__device__ __forceinline__ int half_px(const uint8_t* __restrict__ src, int pitch, int w, int ox, int oy) {
+    const uint8_t* up = src + (2 * oy) * pitch;
+    const uint8_t* lo = up + pitch;
     const int blocks = w >> 4;
     const int paired_out = (blocks >> 1) * 16;
     if (ox < paired_out)

@@ -69,8 +69,14 @@ int  score_tile_rows_max();
 void launch_scores(cudaStream_t, const Geom&, const uint8_t* img, uint8_t* S, unsigned long long* hitmask);
 void launch_row_counts(cudaStream_t, const Geom&, const unsigned long long* hitmask, uint32_t* row_count);
 void launch_fill_candidates(cudaStream_t, const Geom&, const unsigned long long* hitmask, CandBuf);
+// left_done: the per-row strip sums were already written by launch_front
 void launch_integral(cudaStream_t, const Geom&, const uint8_t* img /*layer 0*/, int32_t* integral,
-                     int32_t* left /*F*H*ceil(W/32) scratch*/);
+                     int32_t* left /*F*H*ceil(W/32) scratch*/, bool left_done);
+// the fused front (kernels_front.cu): difference image, pyramid layers 1..5 and the integral's row strip sums in ONE kernel
+// from TMA-staged frame bands; replaces launch_absdiff + launch_pyramid + the first pass of launch_integral for frames up
+// to front_supported() wide
+bool front_supported(const Geom&);
+cudaError_t launch_front(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, uint8_t* img, int32_t* left);
 // --- scans --------------------------------------------------------------------------------------------
 // exclusive scan of data[0..n) in place, data[n] = total; n is a host upper bound, *d_n (optional
 // device value <= n) the live length; scratch holds ceil(n/2048)+1 words

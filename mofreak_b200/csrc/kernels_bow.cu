@@ -7,41 +7,12 @@
 // takes without a tensor map.  Every thread owns one descriptor in registers and streams the codewords as
 // broadcast 128-bit shared loads: 2 XOR + 2 POPC.64 per codeword.  Integer-pipe bound by construction.
 #include "kernels.h"
+#include "tma_device.cuh"
 
 namespace mfk {
 
 constexpr int BOW_THREADS = 256;
 constexpr int BOW_SMEM_WORDS_MAX = 13312;      // 208 KB of codewords per pass
-
-namespace {
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-// one elected thread: arm the barrier with the byte count, then hand the copy to the TMA engine
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-
-}  // namespace
 
 __global__ void __launch_bounds__(BOW_THREADS)
 k_bow_assign(const uint8_t* __restrict__ desc, size_t stride, size_t n_max, const uint32_t* __restrict__ d_n,
@@ -55,7 +26,7 @@ k_bow_assign(const uint8_t* __restrict__ desc, size_t stride, size_t n_max, cons
     uint32_t phase = 0;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
-        if (resident) bulk_load(words, codebook, (uint32_t)K * 16u, &bar);
+        if (resident) { mbar_expect_tx(&bar, (uint32_t)K * 16u); bulk_copy_g2s(words, codebook, (uint32_t)K * 16u, &bar); }
     }
     __syncthreads();
     if (resident) { mbar_wait(&bar, phase); phase ^= 1; }
@@ -74,8 +45,9 @@ k_bow_assign(const uint8_t* __restrict__ desc, size_t stride, size_t n_max, cons
             if (!resident) {
                 __syncthreads();                             // every thread is done with the previous chunk
                 if (threadIdx.x == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic reads before the engine's writes
-                    bulk_load(words, codebook + k0, (uint32_t)kn * 16u, &bar);
+                    fence_proxy_async();                                             // generic reads before the engine's writes
+                    mbar_expect_tx(&bar, (uint32_t)kn * 16u);
+                    bulk_copy_g2s(words, codebook + k0, (uint32_t)kn * 16u, &bar);
                 }
                 mbar_wait(&bar, phase); phase ^= 1;
             }

@@ -148,7 +148,7 @@ __global__ void k_half(const uint8_t* __restrict__ src_base, uint8_t* __restrict
         // the columns of the odd trailing block and of the leftover follow per-column rules: ONE of them per thread, so
         // that the slow path runs once in the row's last warp instead of four times in a row
         const int ox = paired_out + (t - quads);
-        if (ox < dw) row[ox] = (uint8_t)half_px(src, sw, ox, oy);
+        if (ox < dw) row[ox] = (uint8_t)half_px(src, sw, sw, ox, oy);
     }
 }
 
@@ -533,10 +533,10 @@ k_integral_strips(const uint8_t* __restrict__ img, const int32_t* __restrict__ l
     }
 }
 
-void launch_integral(cudaStream_t st, const Geom& g, const uint8_t* img, int32_t* integral, int32_t* left) {
+void launch_integral(cudaStream_t st, const Geom& g, const uint8_t* img, int32_t* integral, int32_t* left, bool left_done) {
     const int strips = (g.W + IG_STRIP - 1) / IG_STRIP;
     const int warps1 = g.F * g.H;
-    k_integral_left<<<(warps1 * 32 + 255) / 256, 256, 0, st>>>(img, left, g.W, g.H, g.F, strips);
+    if (!left_done) k_integral_left<<<(warps1 * 32 + 255) / 256, 256, 0, st>>>(img, left, g.W, g.H, g.F, strips);
     const int warps2 = g.F * strips;
     const int blocks = (warps2 + IG_WARPS - 1) / IG_WARPS;
     if ((((uintptr_t)img | (uintptr_t)g.W) & 3) == 0) k_integral_strips<true><<<blocks, IG_WARPS * 32, 0, st>>>(img, left, integral, g.W, g.H, g.F, strips);

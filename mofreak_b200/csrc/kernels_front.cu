@@ -1,0 +1,233 @@
+// Fused dense front of a launch sequence, one kernel instead of seven:
+//   |I_t - I_{t-5}|              cv::absdiff                                  MoFREAKUtilities.cpp:413-414
+//   pyramid layers 1..5          BriskLayer::twothirdsample / halfsample     brisk.cpp:1840-2065, driven as :572-588
+//   per-row strip sums of layer 0 for the integral image (cv::integral inside cv::FREAK::compute)
+// A block owns a BAND of 12 source rows of one frame pair: 12 = lcm of the samplers' row groups (3 for the two-third
+// sampler, 2 for each of the three halvings), so that every output row of every layer depends on rows of ONE band:
+//   L0 12 rows -> L1 8 -> L3 4 -> L5 2,   L0 12 -> L2 6 -> L4 3.
+// The two frames' bands are staged in shared memory - when the frame width is a multiple of 16 by two bulk copies of the
+// TMA engine (cp.async.bulk, 12 x W contiguous bytes each, completion on an mbarrier; SASS UBLKCP), else by aligned word
+// reads - the difference is taken in place, and all six layers and the row sums are produced from shared memory: the
+// frames are read once and every pyramid byte is written once.  (The separate kernels read layer 0 four times and
+// layers 1..3 twice.)  The samplers' column rules (SSE blocks, tails, quirks) are those of dense_device.cuh.
+#include "brisk_device.cuh"
+#include "dense_device.cuh"
+#include "kernels.h"
+#include "tma_device.cuh"
+
+namespace mfk {
+
+namespace {
+
+constexpr int FR_BAND = 12;
+constexpr int FR_THREADS = 256;
+constexpr int FR_MAX_W = 2048;            // wider frames take the separate kernels (shared memory per band)
+constexpr int IG_STRIP_W = 128;           // strip width of k_integral_strips (kernels_dense.cu)
+
+struct FrontLayout {                      // shared-memory plan of one band
+    int pitch[N_LAYERS];                  // row pitch of each layer's band, a multiple of 16
+    int off[N_LAYERS];                    // byte offsets: layer 0 = current frame (becomes the difference), then layers 1..5
+    int off_prev;                         // previous frame's band
+    int total;
+};
+
+// rows * w bytes from shared rows of pitch sp to global rows of pitch w (dense), widest stores the alignment allows
+__device__ __forceinline__ void copy_out(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int sp, int w, int rows, int tid) {
+    if (rows <= 0) return;
+    if (sp == w && (((uintptr_t)dst) & 15) == 0) {
+        const uint4* s = reinterpret_cast<const uint4*>(src);
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        const int n = rows * w / 16;                        // sp == w is a multiple of 16
+        for (int i = tid; i < n; i += FR_THREADS) d[i] = s[i];
+    } else if (((((uintptr_t)dst) | (uintptr_t)w) & 3) == 0) {
+        const int words = w >> 2;
+        for (int i = tid; i < rows * words; i += FR_THREADS) {
+            const int r = i / words, k = i - r * words;
+            reinterpret_cast<uint32_t*>(dst + (size_t)r * w)[k] = reinterpret_cast<const uint32_t*>(src + r * sp)[k];
+        }
+    } else {
+        for (int i = tid; i < rows * w; i += FR_THREADS) {
+            const int r = i / w, x = i - r * w;
+            dst[(size_t)r * w + x] = src[r * sp + x];
+        }
+    }
+}
+
+// BriskLayer::halfsample on `rows` destination rows: source rows 2j, 2j+1 of a shared band (width sw, pitch sp) ->
+// shared rows of pitch dp.  Inside the paired 16-byte blocks four outputs come from two 8-byte reads per source row
+// (avg of avg, rounding up); the columns of an odd trailing block and of the leftover follow half_px's per-column rules.
+__device__ __forceinline__ void half_band(const uint8_t* __restrict__ src, int sp, int sw, uint8_t* __restrict__ dst, int dp, int dw,
+                                          int rows, int tid) {
+    if (rows <= 0) return;
+    const int paired_out = ((sw >> 4) >> 1) * 16;
+    const int quads = paired_out >> 2;
+    const int items = quads + (dw - paired_out);
+    for (int i = tid; i < rows * items; i += FR_THREADS) {
+        const int j = i / items, t = i - j * items;
+        if (t < quads) {
+            const uint2 u = *reinterpret_cast<const uint2*>(src + (2 * j) * sp + 8 * t);
+            const uint2 l = *reinterpret_cast<const uint2*>(src + (2 * j + 1) * sp + 8 * t);
+            const uint32_t v0 = __vavgu4(u.x, l.x), v1 = __vavgu4(u.y, l.y);
+            const uint32_t ev = __byte_perm(v0, v1, 0x6420), od = __byte_perm(v0, v1, 0x7531);
+            *reinterpret_cast<uint32_t*>(dst + j * dp + 4 * t) = __vavgu4(ev, od);
+        } else {
+            const int ox = paired_out + (t - quads);
+            dst[j * dp + ox] = (uint8_t)half_px(src, sp, sw, ox, j);
+        }
+    }
+}
+
+// BriskLayer::twothirdsample on `groups` row triples of a shared band: one 3x3 source block -> 2x2 outputs per thread
+__device__ __forceinline__ void twothird_band(const uint8_t* __restrict__ src, int sp, int sw, uint8_t* __restrict__ dst, int dp, int dw,
+                                              int groups, int tid) {
+    if (groups <= 0) return;
+    const int triples = dw >> 1;
+    const int blocks = sw / 15;
+    for (int i = tid; i < groups * triples; i += FR_THREADS) {
+        const int gt = i / triples, tc = i - gt * triples;
+        const uint8_t* r1 = src + (3 * gt) * sp + 3 * tc;
+        const uint8_t* r2 = r1 + sp;
+        const uint8_t* r3 = r2 + sp;
+        uint8_t* d1 = dst + (2 * gt) * dp + 2 * tc;
+        uint8_t* d2 = d1 + dp;
+        const int a0 = r1[0], a1 = r1[1], a2 = r1[2], b0 = r2[0], b1 = r2[1], b2 = r2[2], c0 = r3[0], c1 = r3[1], c2 = r3[2];
+        if (tc < 5 * blocks) {
+            // inside a 15-column block: avg(avg(a,b),a) chains, vertically then horizontally; the fifth triple takes its
+            // middle sample from the block's byte 12, i.e. from its own first column (brisk.cpp:1982-1983)
+            const bool fifth = (tc % 5) == 4;
+            const int u0 = avg_up(avg_up(a0, b0), a0), u2 = avg_up(avg_up(a2, b2), a2);
+            const int l0 = avg_up(avg_up(c0, b0), c0), l2 = avg_up(avg_up(c2, b2), c2);
+            const int um = fifth ? u0 : avg_up(avg_up(a1, b1), a1);
+            const int lm = fifth ? l0 : avg_up(avg_up(c1, b1), c1);
+            d1[0] = (uint8_t)avg_up(avg_up(u0, um), u0); d1[1] = (uint8_t)avg_up(avg_up(u2, um), u2);
+            d2[0] = (uint8_t)avg_up(avg_up(l0, lm), l0); d2[1] = (uint8_t)avg_up(avg_up(l2, lm), l2);
+        } else {
+            // trailing triples: (4A + 2(B+C) + D) / 9 (brisk.cpp:2036-2051)
+            d1[0] = (uint8_t)((4 * a0 + 2 * (a1 + b0) + b1) / 9); d1[1] = (uint8_t)((4 * a2 + 2 * (a1 + b2) + b1) / 9);
+            d2[0] = (uint8_t)((4 * c0 + 2 * (c1 + b0) + b1) / 9); d2[1] = (uint8_t)((4 * c2 + 2 * (c1 + b2) + b1) / 9);
+        }
+    }
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(FR_THREADS)
+k_front(const __grid_constant__ Geom g, const __grid_constant__ FrontLayout fl, const uint8_t* __restrict__ store, int store_frames,
+        PairList pl, uint8_t* __restrict__ img_all, int32_t* __restrict__ left, int strips) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ __align__(8) uint64_t bar;
+    const int band = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const int W = g.W, H = g.H;
+    const int y0 = band * FR_BAND, rows = min(FR_BAND, H - y0);
+    uint8_t* A = sm + fl.off[0];
+    uint8_t* B = sm + fl.off_prev;
+    const int p0 = fl.pitch[0];
+    const uint8_t* cur = store + (size_t)(pl.cur_slot[f] % store_frames) * g.L[0].px + (size_t)y0 * W;
+    const uint8_t* prv = store + (size_t)(pl.prev_slot[f] % store_frames) * g.L[0].px + (size_t)y0 * W;
+    // ---- stage the two bands ----
+    if (TMA) {                                   // W % 16 == 0: p0 == W, a band is rows * W contiguous, 16-byte aligned bytes
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            const uint32_t bytes = (uint32_t)(rows * W);
+            mbar_expect_tx(&bar, 2 * bytes);
+            bulk_copy_g2s(A, cur, bytes, &bar);
+            bulk_copy_g2s(B, prv, bytes, &bar);
+        }
+        __syncthreads();                         // the initialised barrier is visible to the waiters
+        mbar_wait(&bar, 0);
+    } else {
+        const int words = (W + 3) >> 2;
+        for (int i = tid; i < rows * words; i += FR_THREADS) {
+            const int r = i / words, k = i - r * words;
+            reinterpret_cast<uint32_t*>(A + r * p0)[k] = load4(cur + (size_t)r * W + 4 * k);
+            reinterpret_cast<uint32_t*>(B + r * p0)[k] = load4(prv + (size_t)r * W + 4 * k);
+        }
+        __syncthreads();
+    }
+    // ---- |a - b| in place ----
+    {
+        uint4* a4 = reinterpret_cast<uint4*>(A);
+        const uint4* b4 = reinterpret_cast<const uint4*>(B);
+        const int n = rows * p0 / 16;
+        for (int i = tid; i < n; i += FR_THREADS) {
+            uint4 u = a4[i];
+            const uint4 v = b4[i];
+            u.x = __vabsdiffu4(u.x, v.x); u.y = __vabsdiffu4(u.y, v.y); u.z = __vabsdiffu4(u.z, v.z); u.w = __vabsdiffu4(u.w, v.w);
+            a4[i] = u;
+        }
+    }
+    __syncthreads();
+    // ---- layer 0 out, its row strip sums, layers 1 and 2 into shared memory ----
+    copy_out(img_all + g.L[0].base + (size_t)f * g.L[0].px + (size_t)y0 * W, A, p0, W, rows, tid);
+    {
+        // left[y][s] = sum of the row's pixels left of 128-column strip s (what k_integral_strips starts each row from)
+        const int lane = tid & 31;
+        for (int r = tid >> 5; r < rows; r += FR_THREADS / 32) {
+            int32_t* out = left + ((size_t)f * H + y0 + r) * strips;
+            int carry = 0;
+            for (int s = 0; s < strips; s++) {
+                const int x = s * IG_STRIP_W + 4 * lane;
+                uint32_t v = 0;
+                if (x < W) {
+                    v = *reinterpret_cast<const uint32_t*>(A + r * p0 + x);
+                    if (x + 4 > W) v &= (1u << (8 * (W - x))) - 1u;
+                }
+                int sum = (int)__dp4a(v, 0x01010101u, 0u);
+#pragma unroll
+                for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+                if (lane == 0) out[s] = carry;
+                carry += sum;
+            }
+        }
+    }
+    uint8_t* S1 = sm + fl.off[1]; uint8_t* S2 = sm + fl.off[2]; uint8_t* S3 = sm + fl.off[3];
+    uint8_t* S4 = sm + fl.off[4]; uint8_t* S5 = sm + fl.off[5];
+    // rows of each layer this band produces (the layers' heights are not multiples of the band's share in general)
+    const int n1 = min(8, g.L[1].h - 8 * band), n2 = min(6, g.L[2].h - 6 * band), n3 = min(4, g.L[3].h - 4 * band);
+    const int n4 = min(3, g.L[4].h - 3 * band), n5 = min(2, g.L[5].h - 2 * band);
+    twothird_band(A, p0, W, S1, fl.pitch[1], g.L[1].w, n1 > 0 ? n1 / 2 : 0, tid);
+    half_band(A, p0, W, S2, fl.pitch[2], g.L[2].w, n2, tid);
+    __syncthreads();
+    copy_out(img_all + g.L[1].base + (size_t)f * g.L[1].px + (size_t)(8 * band) * g.L[1].w, S1, fl.pitch[1], g.L[1].w, n1, tid);
+    copy_out(img_all + g.L[2].base + (size_t)f * g.L[2].px + (size_t)(6 * band) * g.L[2].w, S2, fl.pitch[2], g.L[2].w, n2, tid);
+    half_band(S1, fl.pitch[1], g.L[1].w, S3, fl.pitch[3], g.L[3].w, n3, tid);
+    half_band(S2, fl.pitch[2], g.L[2].w, S4, fl.pitch[4], g.L[4].w, n4, tid);
+    __syncthreads();
+    copy_out(img_all + g.L[3].base + (size_t)f * g.L[3].px + (size_t)(4 * band) * g.L[3].w, S3, fl.pitch[3], g.L[3].w, n3, tid);
+    copy_out(img_all + g.L[4].base + (size_t)f * g.L[4].px + (size_t)(3 * band) * g.L[4].w, S4, fl.pitch[4], g.L[4].w, n4, tid);
+    half_band(S3, fl.pitch[3], g.L[3].w, S5, fl.pitch[5], g.L[5].w, n5, tid);
+    __syncthreads();
+    copy_out(img_all + g.L[5].base + (size_t)f * g.L[5].px + (size_t)(2 * band) * g.L[5].w, S5, fl.pitch[5], g.L[5].w, n5, tid);
+}
+
+}  // namespace
+
+bool front_supported(const Geom& g) { return g.W <= FR_MAX_W; }
+
+cudaError_t launch_front(cudaStream_t st, const Geom& g, const uint8_t* store, int store_frames, PairList pl, uint8_t* img, int32_t* left) {
+    FrontLayout fl;
+    static const int band_rows[N_LAYERS] = {12, 8, 6, 4, 3, 2};
+    int at = 0;
+    for (int l = 0; l < N_LAYERS; l++) {
+        fl.pitch[l] = (g.L[l].w + 15) & ~15;
+        fl.off[l] = at;
+        at += band_rows[l] * fl.pitch[l];
+        if (l == 0) { fl.off_prev = at; at += band_rows[0] * fl.pitch[0]; }
+    }
+    fl.total = at;
+    const int strips = (g.W + IG_STRIP_W - 1) / IG_STRIP_W;
+    const dim3 grid((g.H + FR_BAND - 1) / FR_BAND, g.F);
+    const bool tma = (g.W & 15) == 0;            // slots, bands and rows then start 16-byte aligned and a band is a multiple of 16 bytes
+    cudaError_t e;
+    if (tma) {
+        e = cudaFuncSetAttribute(k_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fl.total);
+        if (e != cudaSuccess) return e;
+        k_front<true><<<grid, FR_THREADS, fl.total, st>>>(g, fl, store, store_frames, pl, img, left, strips);
+    } else {
+        e = cudaFuncSetAttribute(k_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fl.total);
+        if (e != cudaSuccess) return e;
+        k_front<false><<<grid, FR_THREADS, fl.total, st>>>(g, fl, store, store_frames, pl, img, left, strips);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace mfk

@@ -12,6 +12,8 @@
 //            decided completely (scans above/below, refinement, keypoint record);
 //   phase B  one block per pair: the few candidates with ties, layer by layer, by a fixed point whose only
 //            ordering requirement is "every raster-earlier undecided tie candidate within 3 px is final".
+#include <stdlib.h>
+
 #include "sparse_device.cuh"
 
 namespace mfk {
@@ -151,17 +153,43 @@ void launch_phase_a(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTa
 }
 
 // ---------------------------------------------------------------------------------------------------
-// phase B: one block per pair
+// phase B: a group of G threads per pair, 256 / G pairs per block
 // ---------------------------------------------------------------------------------------------------
+// The tie candidates of a pair are few (about pyramid pixels / 1000: ~36 at 160x120, ~760 at 720x576) and their fixed
+// point is a chain of short rounds, i.e. latency: what a pair needs is cheap barriers and many pairs in flight, not
+// threads.  So the group size follows the frame size - one WARP per pair for small frames (__syncwarp, eight pairs per
+// block), named barriers for 64 / 128 threads, the whole block (__syncthreads) for large frames.
 constexpr int PB_THREADS = 256;
-constexpr int PB_LIST = PEND_CAP;  // tie candidates of one (pair, layer) staged in shared memory per sweep
+constexpr int PB_LIST = PEND_CAP;  // tie candidates of one (pair, layer) staged in shared memory per sweep, for G = 256
 
+template <int G>
+__device__ __forceinline__ void group_sync(int grp) {
+    if (G == 32) __syncwarp();
+    else if (G == PB_THREADS) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "r"(G) : "memory");
+}
+
+template <int G>
 __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
-    __shared__ uint32_t list[2][PB_LIST];       // undecided tie candidates of this round / of the next round
-    __shared__ uint32_t passed[PB_LIST];        // this round's winners, re-packed so that the scans run on full warps
-    __shared__ uint8_t verdict[PB_LIST];
-    __shared__ int n_list, n_next, n_pass, more;
-    PairView pv; pv.g = &g; pv.m = m; pv.f = blockIdx.x;
+    constexpr int PER = PB_THREADS / G;          // pairs per block
+    constexpr int LIST = PB_LIST / PER;          // list capacity of one pair
+    __shared__ uint32_t list_s[PER][2][LIST];    // undecided tie candidates of this round / of the next round
+    __shared__ uint32_t passed_s[PER][LIST];     // this round's winners, re-packed so that the scans run on full warps
+    __shared__ uint8_t verdict_s[PER][LIST];
+    __shared__ int ctl[PER][4];                  // n_list, n_next, n_pass, more
+    __shared__ int warp_cnt[PB_THREADS / 32];
+    const int grp = threadIdx.x / G, t = threadIdx.x % G;
+    const int f = blockIdx.x * PER + grp;
+    if (f >= g.F) return;                        // whole groups leave; every barrier below is per group
+    uint32_t (*list)[LIST] = list_s[grp];
+    uint32_t* passed = passed_s[grp];
+    uint8_t* verdict = verdict_s[grp];
+    volatile int& n_list = ctl[grp][0];
+    volatile int& n_next = ctl[grp][1];
+    volatile int& n_pass = ctl[grp][2];
+    volatile int& more = ctl[grp][3];
+    int* const wc = warp_cnt + grp * (G / 32);
+    PairView pv; pv.g = &g; pv.m = m; pv.f = f;
     const uint32_t cap = (uint32_t)g.cand_cap;
     for (int li = 0; li < N_LAYERS; li++) {
         const LayerGeom& L = g.L[li];
@@ -170,56 +198,55 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
         uint32_t cursor = begin;
         const uint32_t n_pending = cb.pend_count[pv.f * N_LAYERS + li];
         if (n_pending == 0) continue;
-        const bool listed = n_pending <= PEND_CAP;      // phase A's list holds them all (order is irrelevant then)
+        const bool listed = n_pending <= (uint32_t)min((int)PEND_CAP, LIST);      // phase A's list holds them all and they fit (order is irrelevant then)
         // candidates are in raster order, so taking the pending ones chunk by chunk keeps every dependency
         // (always raster-earlier) inside the current or an already finished chunk
         int again;                                      // `more`, read by every thread BEFORE thread 0 may clear it again
         do {
-            if (threadIdx.x == 0) { n_list = 0; more = 0; }
-            __syncthreads();
+            if (t == 0) { n_list = 0; more = 0; }
+            group_sync<G>(grp);
             uint32_t next_cursor = end;
             if (listed) {
                 const uint32_t* src = cb.pend_list + (size_t)(pv.f * N_LAYERS + li) * PEND_CAP;
-                for (uint32_t i = threadIdx.x; i < n_pending; i += PB_THREADS) list[0][i] = src[i];
-                if (threadIdx.x == 0) n_list = (int)n_pending;
+                for (uint32_t i = t; i < n_pending; i += G) list[0][i] = src[i];
+                if (t == 0) n_list = (int)n_pending;
             } else
-            // gather up to PB_LIST pending candidates starting at cursor, preserving order
-            for (uint32_t base = cursor; base < end; base += PB_THREADS) {
-                const uint32_t c = base + threadIdx.x;
+            // gather up to LIST pending candidates starting at cursor, preserving order
+            for (uint32_t base = cursor; base < end; base += G) {
+                const uint32_t c = base + t;
                 const bool pend = c < end && (cb.flags[c] & ST_PENDING);
                 // ordered append: warp ballots + per-warp offsets
-                __shared__ int warp_cnt[PB_THREADS / 32];
                 const unsigned bal = __ballot_sync(0xffffffffu, pend);
-                if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(bal);
-                __syncthreads();
+                if ((t & 31) == 0) wc[t >> 5] = __popc(bal);
+                group_sync<G>(grp);
                 int before = n_list;
-                for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before += warp_cnt[w];
+                for (int w = 0; w < (int)(t >> 5); w++) before += wc[w];
                 int total = 0;
-                for (int w = 0; w < PB_THREADS / 32; w++) total += warp_cnt[w];
-                const int slot = before + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
-                const bool fits = n_list + total <= PB_LIST;
+                for (int w = 0; w < G / 32; w++) total += wc[w];
+                const int slot = before + __popc(bal & ((1u << (t & 31)) - 1u));
+                const bool fits = n_list + total <= LIST;
                 if (pend && fits) list[0][slot] = c;
-                __syncthreads();
-                if (!fits) { next_cursor = base; if (threadIdx.x == 0) more = 1; break; }
-                if (threadIdx.x == 0) n_list += total;
-                __syncthreads();
+                group_sync<G>(grp);
+                if (!fits) { next_cursor = base; if (t == 0) more = 1; break; }
+                if (t == 0) n_list += total;
+                group_sync<G>(grp);
             }
-            __syncthreads();
+            group_sync<G>(grp);
             // fixed point over this chunk: every round decides all candidates whose raster-earlier tie neighbours are
             // final (from the previous round's statuses), re-packs the winners and the still-waiting ones, then runs the
             // scans of the winners one per thread
             int nl = n_list, cur = 0;
 #ifdef MFK_PB_STATS
             int rounds = 0;
-            if (threadIdx.x == 0) atomicAdd(&cb.counters[5], (uint32_t)nl);
+            if (t == 0) atomicAdd(&cb.counters[5], (uint32_t)nl);
 #endif
             while (nl > 0) {
 #ifdef MFK_PB_STATS
                 rounds++;
-                if (threadIdx.x == 0) { atomicAdd(&cb.counters[4], 1u); atomicAdd(&cb.counters[7], (uint32_t)nl); }
+                if (t == 0) { atomicAdd(&cb.counters[4], 1u); atomicAdd(&cb.counters[7], (uint32_t)nl); }
 #endif
-                if (threadIdx.x == 0) { n_next = 0; n_pass = 0; }
-                for (int i = threadIdx.x; i < nl; i += PB_THREADS) {
+                if (t == 0) { n_next = 0; n_pass = 0; }
+                for (int i = t; i < nl; i += G) {
                     const uint32_t c = list[cur][i];
                     const uint32_t xy = cb.xy[c];
                     const int x = xy & 0xffff, y = xy >> 16;
@@ -227,42 +254,58 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
                     tw.load(pv, li, x, y);
                     verdict[i] = earlier_pending_nearby(tw) ? 0 : (tie_break(tw) ? 2 : 1);
                 }
-                __syncthreads();
-                for (int i = threadIdx.x; i < nl; i += PB_THREADS) {
+                group_sync<G>(grp);
+                for (int i = t; i < nl; i += G) {
                     const uint32_t c = list[cur][i];
                     const uint8_t v = verdict[i];
-                    if (v == 0) list[cur ^ 1][atomicAdd(&n_next, 1)] = c;          // still waiting (order is irrelevant)
-                    else if (v == 2) passed[atomicAdd(&n_pass, 1)] = c;
+                    if (v == 0) list[cur ^ 1][atomicAdd(&ctl[grp][1], 1)] = c;          // still waiting (order is irrelevant)
+                    else if (v == 2) passed[atomicAdd(&ctl[grp][2], 1)] = c;
                     else {
                         const uint32_t xy = cb.xy[c];
                         pv.m.status[pv.off(li) + (xy >> 16) * L.w + (xy & 0xffff)] = 0; cb.flags[c] = 0;
                     }
                 }
-                __syncthreads();
-                for (int i = threadIdx.x; i < n_pass; i += PB_THREADS) {
+                group_sync<G>(grp);
+                const int np = n_pass;
+                for (int i = t; i < np; i += G) {
                     const uint32_t c = passed[i];
                     const uint32_t xy = cb.xy[c];
                     after_max2d(pv, cb, tb, li, xy & 0xffff, xy >> 16, c);
                 }
                 __threadfence_block();
-                __syncthreads();
+                group_sync<G>(grp);
                 nl = n_next; cur ^= 1;
-                __syncthreads();
+                group_sync<G>(grp);
             }
 #ifdef MFK_PB_STATS
-            if (threadIdx.x == 0) atomicMax(&cb.counters[6], (uint32_t)rounds);
+            if (t == 0) atomicMax(&cb.counters[6], (uint32_t)rounds);
 #endif
             cursor = next_cursor;
             again = more;
-            __syncthreads();
+            group_sync<G>(grp);
         } while (again);
         __threadfence();        // seen marks of layer li+1 are complete before its ties are examined
-        __syncthreads();
+        group_sync<G>(grp);
     }
 }
 
+int phase_b_group(const Geom& g) {
+    if (const char* e = getenv("MFK_PB_GROUP")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) return v; }
+    // Measured in the pipelined bench (four launch sequences in flight): small groups win at every frame size, although a
+    // pair then takes longer on its own - 720x576: G = 256 106.2 k frames/s, 128 112.4 k, 64 116.5 k, 32 116.3 k; 320x240: 64
+    // 541 k, 32 572 k; 160x120: 64 1.83 M, 32 2.04 M.  The kernel waits on memory most of the time; fewer resident warps
+    // per pair leave the SMs' registers and issue slots to the dense kernels of the other launch sequences.
+    const int ties = g.pyr_px / 1000;            // expected tie candidates per pair
+    return ties <= 400 ? 32 : 64;
+}
+
 void launch_phase_b(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTables tb) {
-    k_phase_b<<<g.F, PB_THREADS, 0, st>>>(g, m, cb, tb);
+    switch (phase_b_group(g)) {
+        case 32:  k_phase_b<32><<<(g.F + 7) / 8, PB_THREADS, 0, st>>>(g, m, cb, tb); break;
+        case 64:  k_phase_b<64><<<(g.F + 3) / 4, PB_THREADS, 0, st>>>(g, m, cb, tb); break;
+        case 128: k_phase_b<128><<<(g.F + 1) / 2, PB_THREADS, 0, st>>>(g, m, cb, tb); break;
+        default:  k_phase_b<256><<<g.F, PB_THREADS, 0, st>>>(g, m, cb, tb); break;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -21,6 +21,9 @@
 //                        (MoFREAKUtilities.cpp:374-498) and the .mofreak writer (:691-719).
 //   bow_restate.cpp      bruteForceMatch / hammingDistance / buildHistogram / loadClusters
 //                        (BagOfWordsRepresentation.cpp:22-173).
+//   sliding_restate.cpp  computeSlidingBagOfWords (BagOfWordsRepresentation.cpp:176-378), SURVEY 8(f) N2.
+//   cluster_restate.cpp  shuffleCVMat / randomClusters / writeClusters (Clustering.cpp:6-25, 165-213, 233-257) with the
+//                        random numbers injected, SURVEY 8(f) N3.
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
@@ -100,5 +103,14 @@ int  brute_force_match(const uint8_t desc[16], const uint8_t* codebook, int K); 
 std::vector<uint8_t> load_clusters_text(const std::string& text);
 // .mofreak text -> normalised histogram (:74-138); returns false for an empty file.
 bool build_histogram(const std::string& mofreak_text, const uint8_t* codebook, int K, std::vector<float>& hist);
+
+// ---- "next" rows of SURVEY 8(f) -------------------------------------------------------------------
+// TRECVID sliding-window bag of words (:176-378): text of the libsvm lines written for one `.mofreak` file
+std::string sliding_bag_of_words(const std::string& mofreak_text, const uint8_t* codebook, int K, int alpha, int label);
+// codebook selection (Clustering.cpp) with injected random numbers; see cluster_restate.cpp
+size_t shuffle_rows(uint8_t* data, int rows, int cols, const int* rands);
+size_t random_clusters(uint8_t* data, int rows, int dim, int num_clusters, int num_classes, const int* classes, int n_classes,
+                       bool only_one_class, const int* rands, uint8_t* centers, int* center_row);
+std::string clusters_text(const uint8_t* centers, int num_clusters, int dim);
 
 }  // namespace orc

@@ -160,4 +160,22 @@ int orc_build_histogram(const char* text, long len, const uint8_t* codebook, int
     return ok ? 1 : 0;
 }
 
+// TRECVID sliding window (sliding_restate.cpp): two-call protocol, returns the text length
+long orc_sliding_bow(const char* text, long len, const uint8_t* codebook, int K, int alpha, int label, char* out, long cap) {
+    const std::string s = sliding_bag_of_words(std::string(text, (size_t)len), codebook, K, alpha, label);
+    if (out && cap > 0) memcpy(out, s.data(), (size_t)((long)s.size() < cap ? (long)s.size() : cap));
+    return (long)s.size();
+}
+
+// codebook selection (cluster_restate.cpp): data is shuffled in place; returns the random draws consumed
+long orc_random_clusters(uint8_t* data, int rows, int dim, int num_clusters, int num_classes, const int* classes, int n_classes,
+                         int only_one_class, const int* rands, uint8_t* centers, int* center_row) {
+    return (long)random_clusters(data, rows, dim, num_clusters, num_classes, classes, n_classes, only_one_class != 0, rands, centers, center_row);
+}
+long orc_clusters_text(const uint8_t* centers, int num_clusters, int dim, char* out, long cap) {
+    const std::string s = clusters_text(centers, num_clusters, dim);
+    if (out && cap > 0) memcpy(out, s.data(), (size_t)((long)s.size() < cap ? (long)s.size() : cap));
+    return (long)s.size();
+}
+
 }  // extern "C"

@@ -76,7 +76,7 @@ struct Harness {
             for (int y = 0; y < D.h; y++)
                 for (int x = 0; x < D.w; x++)
                     img[D.base + y * D.w + x] = (uint8_t)(l == 1 ? twothird_px(img.data() + Sg.base, Sg.w, x, y)
-                                                                 : half_px(img.data() + Sg.base, Sg.w, x, y));
+                                                                 : half_px(img.data() + Sg.base, Sg.w, Sg.w, x, y));
         }
         row_count.assign(g.rows + 1, 0);
         xy.clear(); meta.clear();

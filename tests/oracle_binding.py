@@ -197,6 +197,39 @@ class Oracle:
         ok = self.L.orc_build_histogram(b, C.c_long(len(b)), _p(cb), cb.shape[0], _p(hist))
         return bool(ok), hist
 
+    # ---- SURVEY 8(f) "next" rows ----
+    def sliding_bow(self, text, codebook, alpha, label):
+        cb = np.ascontiguousarray(codebook, np.uint8).reshape(-1, 16)
+        b = text.encode()
+        self.L.orc_sliding_bow.restype = C.c_long
+        n = self.L.orc_sliding_bow(b, C.c_long(len(b)), _p(cb), cb.shape[0], alpha, label, None, C.c_long(0))
+        buf = C.create_string_buffer(n + 1)
+        self.L.orc_sliding_bow(b, C.c_long(len(b)), _p(cb), cb.shape[0], alpha, label, buf, C.c_long(n))
+        return buf.raw[:n].decode()
+
+    def random_clusters(self, data, num_clusters, num_classes, classes, only_one_class, rands, centers=None, center_row=0):
+        """data: [rows, dim + 3] uint8 (copied, shuffled copy returned); rands: the numbers rand() would return."""
+        d = np.ascontiguousarray(data, np.uint8).copy()
+        rows, cols = d.shape
+        cl = np.ascontiguousarray(classes, np.int32)
+        r = np.ascontiguousarray(rands, np.int32)
+        assert r.size >= 3 * max(rows - 1, 0)
+        if centers is None:
+            centers = np.zeros((num_clusters, cols - 3), np.uint8)
+        cr = C.c_int(center_row)
+        self.L.orc_random_clusters.restype = C.c_long
+        used = self.L.orc_random_clusters(_p(d), rows, cols - 3, num_clusters, num_classes, _p(cl), cl.size, 1 if only_one_class else 0,
+                                          _p(r), _p(centers), C.byref(cr))
+        return centers, cr.value, int(used), d
+
+    def clusters_text(self, centers):
+        c = np.ascontiguousarray(centers, np.uint8)
+        self.L.orc_clusters_text.restype = C.c_long
+        n = self.L.orc_clusters_text(_p(c), c.shape[0], c.shape[1], None, C.c_long(0))
+        buf = C.create_string_buffer(n + 1)
+        self.L.orc_clusters_text(_p(c), c.shape[0], c.shape[1], buf, C.c_long(n))
+        return buf.raw[:n].decode()
+
 
 _cached = None
 

@@ -285,6 +285,42 @@ def test_serial_and_pipelined_launch_sequences_agree(orc):
     assert util.rows_equal(a, want) and util.rows_equal(b, want) and util.rows_equal(c, want)
 
 
+def test_wide_frames_take_the_separate_dense_kernels(orc):
+    """Frames wider than the fused front kernel's band buffer (2048 px) run absdiff / pyramid / row sums as separate kernels."""
+    clip = mofreak_b200.synth_clip(2064, 64, 7, 9)
+    want = orc.extract_clip(clip)
+    with mofreak_b200.Context(2064, 64, 8, 2) as ctx:
+        ctx.profile_enable(True)
+        got = ctx.extract_clip(clip)
+        prof = ctx.profile_read()
+    assert len(want) > 0 and util.rows_equal(got, want), util.describe_diff(got, want)
+    assert prof["front"][0] == 0 and prof["pyramid"][0] == 5 and prof["absdiff"][0] == 1
+
+
+@pytest.mark.parametrize("shape", [(720, 576), (212, 163), (100, 58)])
+def test_fused_front_equals_separate_dense_kernels(orc, shape, monkeypatch):
+    """The fused front (TMA-staged bands when the width is a multiple of 16, word reads otherwise; partial last band) and
+    the separate kernels produce the same pyramid, hence the same rows."""
+    w, h = shape
+    clip = mofreak_b200.synth_clip(w, h, 8, 17)
+    layers = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("MFK_FUSED_FRONT", fused)
+        with mofreak_b200.Context(w, h, 8, 3) as ctx:
+            ctx.upload_frames(clip, 0)
+            ctx.profile_enable(True)
+            ctx.extract_pairs(np.array([5, 6, 7], np.int32), np.array([0, 1, 2], np.int32), np.array([4, 5, 6], np.int32))
+            rows, _ = ctx.fetch_rows(100000, 3)
+            prof = ctx.profile_read()
+            assert (prof["front"][0] == 1) == (fused == "1")
+            layers[fused] = ([ctx.debug_layer(0, l, p) for l in range(6) for p in range(3)], rows.copy())
+    for a, b in zip(layers["1"][0], layers["0"][0]):
+        assert np.array_equal(a, b)
+    assert util.rows_equal(layers["1"][1], layers["0"][1])
+    want = orc.extract_clip(clip)
+    assert util.rows_equal(layers["1"][1], want)
+
+
 def test_timer_and_profile_hooks():
     clip = mofreak_b200.synth_clip(160, 120, 9, 301)
     with mofreak_b200.Context(160, 120, 16, 4) as ctx:
@@ -296,8 +332,8 @@ def test_timer_and_profile_hooks():
         ctx.extract_pairs(cur, cur - 5, cur - 1)
         ms = ctx.timer_stop()
         prof = ctx.profile_read()
-        assert ms > 0 and ctx.launch_count() - before == 27
-        assert prof["scores"][0] == 1 and prof["scores"][1] > 0 and prof["describe"][1] > 0
+        assert ms > 0 and ctx.launch_count() - before == 21      # one launch sequence: 21 kernels with the fused front
+        assert prof["scores"][0] == 1 and prof["scores"][1] > 0 and prof["describe"][1] > 0 and prof["front"][0] == 1
 
 
 @pytest.mark.gpu
