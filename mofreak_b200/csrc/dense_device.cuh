@@ -88,4 +88,23 @@ __device__ __forceinline__ int oast_score_bound_packed(const uint32_t r[16], con
     return max(brighter, darker) - 1;
 }
 
+// The same bound for TWO horizontally adjacent centres at once: r[i] and `centre` hold the 16-bit pixels of the left
+// centre in the low half and of the right centre in the high half.  Both polarities need their own chain here (8 packed
+// max + 8 packed min, then 4 + 4 three-input reductions), which is the same 12 packed operations per pixel as the
+// (v, 255 - v) form, but every operand covers two centres, so the shared-memory loads per pixel halve.
+// Returns, per half, bound + 256 (the bias keeps the packed subtractions free of borrows between the halves).
+__device__ __forceinline__ uint32_t oast_bound_pair(const uint32_t r[16], const uint32_t centre) {
+    uint32_t mx[8], mn[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { mx[j] = __vmaxu2(r[j], r[j + 8]); mn[j] = __vminu2(r[j], r[j + 8]); }
+    const uint32_t a = __vimin3_u16x2(mx[0], mx[1], mx[2]), b = __vimin3_u16x2(mx[3], mx[4], mx[5]);
+    const uint32_t lo = __vminu2(b, __vimin3_u16x2(mx[6], mx[7], a));            // min over the pairs of the pair maxima
+    const uint32_t c = __vimax3_u16x2(mn[0], mn[1], mn[2]), d = __vimax3_u16x2(mn[3], mn[4], mn[5]);
+    const uint32_t hi = __vmaxu2(d, __vimax3_u16x2(mn[6], mn[7], c));            // max over the pairs of the pair minima
+    // brighter: lo - p - 1, darker: p - hi - 1, each half in [-256, 254]; + 256 keeps every half non-negative
+    const uint32_t brighter = lo + 0x00ff00ffu - centre;
+    const uint32_t darker = centre + 0x00ff00ffu - hi;
+    return __vmaxu2(brighter, darker);
+}
+
 }  // namespace mfk

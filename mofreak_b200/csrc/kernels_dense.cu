@@ -201,22 +201,27 @@ void launch_pyramid(cudaStream_t st, const Geom& g, uint8_t* img) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// OAST-9/16 score map + per-row hit counts
+// OAST-9/16 score map + per-row hit masks
 // ---------------------------------------------------------------------------------------------------
 // S_full(p) = clamp(max over the 16 arcs of 9 contiguous ring pixels of min(v_i - p) resp. min(p - v_i), minus
 // 1, to [0, 254]) — the value cornerScore's bisection converges to from b0 = 0 (oast9_16_nms.cc:42-2115), and
-// detect() at threshold b fires exactly where S_full >= b (oast9_16.cc:46).  Each pixel is staged in shared
-// memory as the pair (v, 255 - v) in the two 16-bit halves of a word, so ONE 3-input packed minimum
-// (VIMNMX3.U16x2) serves the brighter and the darker test at once:
-//     min_k v_k - p            = low  half of min_k X_k, minus p
-//     p - max_k v_k            = high half of min_k X_k, minus (255 - p)
-// 16 + 16 packed min3 build all 16 arc minima (windows of 3, then 3 of those), 8 packed max3 reduce them.
-// One launch covers all six layers of all pairs: grid = (tile column, tile row over all layers, pair) of 64x32 tiles.
-// A block of 256 threads (32 x 8) stages the tile plus its 3-px halo (aligned 32-bit global reads, 128-bit shared
-// stores, 4 packed pixels each) and every thread scores 2 x 4 pixels.
+// detect() at threshold b fires exactly where S_full >= b (oast9_16.cc:46).
+// One launch covers all six layers of all pairs: grid = (tile column, tile row over all layers, pair) of 64x32 tiles; a
+// block of 256 threads stages the tile plus its 3-px halo and scores it in two steps:
+//   1. every pixel: the antipodal-pair BOUND  S <= max(min_j max(v_j, v_j+8) - p, p - max_j min(v_j, v_j+8)) - 1  (an arc of 9
+//      contains one pixel of each antipodal pair).  bound <= 0 proves S = 0: most pixels of a difference image.  This
+//      step runs on PAIRS of horizontally adjacent centres packed into the two 16-bit halves of a word
+//      (VIMNMX.U16x2): the tile is staged as 16-bit pixels twice, once aligned to even columns (E) and once to odd
+//      columns (O), so that the ring pixels of BOTH centres at any ring offset are ONE aligned 32-bit shared load -
+//      8.5 loads and 12 packed min/max per pixel (17 and 12 with one centre per word).
+//   2. the survivors (~20 % on noisy difference images), queued per warp so that full warps score them: 17 16-bit loads,
+//      each widened to (v, 255 - v) in the halves of a word, so that ONE 3-input packed minimum (VIMNMX3.U16x2) serves the
+//      brighter and the darker test at once: 16 + 16 packed min3 build the 16 arc minima, 8 packed max3 reduce them.
+// Scores land in a shared 64x32 byte tile that leaves with 32-bit stores (zeros included: no clearing of S); hits
+// (S >= 30) leave as one 64-bit mask per tile row.
 constexpr int SC_TW = 64, SC_TH = 32;                 // output tile
 constexpr int SC_SW = SC_TW + 8, SC_SH = SC_TH + 6;   // staged: columns x0-4 .. x0+67, rows y0-3 .. y0+34
-constexpr int SC_WORDS = SC_SW / 4;                   // aligned words per staged row
+constexpr int SC_PW = SC_SW / 2;                      // 16-bit pixel pairs (words) per staged row
 
 struct ScoreTiles {                         // blockIdx.y = tile row over all layers -> its layer and first image row
     int across[N_LAYERS];
@@ -224,10 +229,24 @@ struct ScoreTiles {                         // blockIdx.y = tile row over all la
     int16_t y0[768];
 };
 
+// 8 pixels (two little-endian words w0, w1 and the byte after them) -> their four even-aligned and four odd-aligned
+// 16-bit pixel pairs
+__device__ __forceinline__ void widen8(uint32_t w0, uint32_t w1, uint32_t w2, uint4& even, uint4& odd) {
+    const uint32_t f0 = __funnelshift_r(w0, w1, 8), f1 = __funnelshift_r(w1, w2, 8);
+    even.x = __byte_perm(w0, 0, 0x4140); even.y = __byte_perm(w0, 0, 0x4342);
+    even.z = __byte_perm(w1, 0, 0x4140); even.w = __byte_perm(w1, 0, 0x4342);
+    odd.x = __byte_perm(f0, 0, 0x4140); odd.y = __byte_perm(f0, 0, 0x4342);
+    odd.z = __byte_perm(f1, 0, 0x4140); odd.w = __byte_perm(f1, 0, 0x4342);
+}
+
 __global__ void __launch_bounds__(256)
 k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tiles, const uint8_t* __restrict__ img_all,
          uint8_t* __restrict__ S_all, unsigned long long* __restrict__ hitmask, int mask_words) {
-    __shared__ __align__(16) uint32_t tile[SC_SH][SC_SW];
+    __shared__ __align__(16) uint32_t E[SC_SH][SC_PW];      // E[r][k] = pixels (2k, 2k+1) of staged row r, 16 bits each
+    __shared__ __align__(16) uint32_t O[SC_SH][SC_PW];      // O[r][k] = pixels (2k+1, 2k+2)
+    __shared__ uint16_t hard[SC_TW * SC_TH];
+    __shared__ unsigned long long row_hits[SC_TH];      // bit x of word y: pixel (x0 + x, y0 + y) is a detector hit
+    __shared__ __align__(16) uint8_t score_tile[SC_TH][SC_TW];
     // grid = (widest layer's tile columns, tile rows of all layers, pairs): no division to find the tile; the blocks
     // beyond a narrower layer's last column leave at once
     const int f = blockIdx.z;
@@ -239,64 +258,49 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     const int w = L.w, h = L.h;
     const uint8_t* img = img_all + L.base + (size_t)f * L.px;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    // ---- stage: word k of staged row r holds pixels x0-4+4k .. x0-1+4k of image row y0-3+r ----
-    for (int i = tid; i < SC_SH * SC_WORDS; i += 256) {
-        const int r = i / SC_WORDS, k = i - r * SC_WORDS;
+    // ---- stage: item (r, j) = 8 pixels x0-4+8j .. of image row y0-3+r (clamped); pixels outside the row read as 0 - they
+    // are only ever ring pixels of border centres, which are not scored ----
+    for (int i = tid; i < SC_SH * (SC_SW / 8); i += 256) {
+        const int r = i / (SC_SW / 8), j = i - r * (SC_SW / 8);
         const int gy = min(max(y0 - 3 + r, 0), h - 1);
-        const int gx = x0 - 4 + 4 * k;
-        // pixels left of the image or right of its last row are never used by a scored (interior) pixel; skip the read
-        uint32_t v = 0;
-        if (gx >= 0 && gx < w) v = load4(img + gy * w + gx);
-        uint4 q;
-        q.x = 0x00ff0000u - (v & 0xffu) * 65535u;                 // b | (255 - b) << 16
-        q.y = 0x00ff0000u - ((v >> 8) & 0xffu) * 65535u;
-        q.z = 0x00ff0000u - ((v >> 16) & 0xffu) * 65535u;
-        q.w = 0x00ff0000u - (v >> 24) * 65535u;
-        *reinterpret_cast<uint4*>(&tile[r][4 * k]) = q;
+        const int gx = x0 - 4 + 8 * j;
+        const uint8_t* p = img + gy * w + gx;
+        const uint32_t w0 = (gx >= 0 && gx < w) ? load4(p) : 0u;
+        const uint32_t w1 = (gx + 4 < w) ? load4(p + 4) : 0u;           // gx + 4 >= 0 always
+        const uint32_t w2 = (gx + 8 < w) ? load4(p + 8) : 0u;
+        uint4 ev, od;
+        widen8(w0, w1, w2, ev, od);
+        *reinterpret_cast<uint4*>(&E[r][4 * j]) = ev;
+        *reinterpret_cast<uint4*>(&O[r][4 * j]) = od;
     }
-    __syncthreads();
-    // ---- score, in two steps so that the 16-arc evaluation only runs where it can matter, on full warps:
-    //   1. every pixel: ring loads + antipodal-pair bound (12 packed ops).  bound <= 0 proves S = 0 (most pixels of a
-    //      difference image: flat or noise).  Each thread remembers which of its 8 pixels are left; one block-wide scan
-    //      then queues them in shared memory.
-    //   2. the queue: full closed-form score (40 packed ops) into a shared score tile, hit mask.
-    // The score tile (zero where nothing was scored) leaves with 32-bit stores.  The kernel sits on the ALU/LSU pipes, so
-    // what counts is instructions per pixel.
-    __shared__ uint16_t hard[SC_TW * SC_TH];
-    __shared__ unsigned long long row_hits[SC_TH];      // bit x of word y: pixel (x0 + x, y0 + y) is a detector hit
-    __shared__ __align__(16) uint8_t score_tile[SC_TH][SC_TW];
     if (tid < SC_TH) row_hits[tid] = 0ull;
     reinterpret_cast<unsigned long long*>(&score_tile[0][0])[tid] = 0ull;          // 256 threads x 8 bytes = the tile
-    const uint32_t* t0 = &tile[threadIdx.y + 3][threadIdx.x + 4];      // centre of this thread's first pixel
-    const int xa = x0 + threadIdx.x, ya = y0 + threadIdx.y;
-    bool in_x[SC_TW / 32];
-#pragma unroll
-    for (int jx = 0; jx < SC_TW / 32; jx++) {
-        const int x = xa + 32 * jx;
-        in_x[jx] = x >= 3 && x < w - 3;
-    }
-    uint32_t mine = 0;                                  // bit 2 * jy + jx: that pixel needs the full score
+    __syncthreads();
+    // ---- step 1: a thread owns the centre pairs (x0 + 2 lane, +1) of rows y0 + ty + 8 jy; staged column of the pair's first
+    // pixel is 4 + 2 lane = word 2 + lane of E ----
+    const int lane = threadIdx.x, wrp = threadIdx.y;
+    const int xa = x0 + 2 * lane;
+    const bool in_lo = xa >= 3 && xa < w - 3, in_hi = xa + 1 >= 3 && xa + 1 < w - 3;
+    uint32_t mine = 0;                                  // bit 2 * jy + half: that pixel needs the full score
 #pragma unroll
     for (int jy = 0; jy < SC_TH / 8; jy++) {
-        const int y = ya + 8 * jy;
-        const bool in_y = y >= 3 && y < h - 3;
-#pragma unroll
-        for (int jx = 0; jx < SC_TW / 32; jx++) {
-            if (!(in_y && in_x[jx])) continue;
-            const uint32_t* c = t0 + (8 * jy) * SC_SW + 32 * jx;
-            // ring in circle order (oast9_16.h:214-232)
-            uint32_t r[16];
-            r[0] = c[-3];                 r[1] = c[-SC_SW - 3];         r[2] = c[-2 * SC_SW - 2];     r[3] = c[-3 * SC_SW - 1];
-            r[4] = c[-3 * SC_SW];         r[5] = c[-3 * SC_SW + 1];     r[6] = c[-2 * SC_SW + 2];     r[7] = c[-SC_SW + 3];
-            r[8] = c[3];                  r[9] = c[SC_SW + 3];          r[10] = c[2 * SC_SW + 2];     r[11] = c[3 * SC_SW + 1];
-            r[12] = c[3 * SC_SW];         r[13] = c[3 * SC_SW - 1];     r[14] = c[2 * SC_SW - 2];     r[15] = c[SC_SW - 3];
-            if (oast_score_bound_packed(r, c[0]) > 0) mine |= 1u << (2 * jy + jx);
-        }
+        const int ly = wrp + 8 * jy;
+        const int y = y0 + ly;
+        if (!(y >= 3 && y < h - 3) || !(in_lo || in_hi)) continue;
+        const uint32_t* e = &E[ly + 3][lane + 2];
+        const uint32_t* o = &O[ly + 3][lane + 2];
+        // ring in circle order (oast9_16.h:214-232); offset dx even -> E[k + dx/2], odd -> O[k + (dx-1)/2]
+        uint32_t r[16];
+        r[0] = o[-2];                 r[1] = o[-SC_PW - 2];         r[2] = e[-2 * SC_PW - 1];     r[3] = o[-3 * SC_PW - 1];
+        r[4] = e[-3 * SC_PW];         r[5] = o[-3 * SC_PW];         r[6] = e[-2 * SC_PW + 1];     r[7] = o[-SC_PW + 1];
+        r[8] = o[1];                  r[9] = o[SC_PW + 1];          r[10] = e[2 * SC_PW + 1];     r[11] = o[3 * SC_PW];
+        r[12] = e[3 * SC_PW];         r[13] = o[3 * SC_PW - 1];     r[14] = e[2 * SC_PW - 1];     r[15] = o[SC_PW - 2];
+        const uint32_t both = oast_bound_pair(r, e[0]);            // halves: bound + 256 of the two centres
+        if (in_lo && (both & 0xffffu) > 256u) mine |= 1u << (2 * jy);
+        if (in_hi && (both >> 16) > 256u) mine |= 1u << (2 * jy + 1);
     }
     // Each warp queues its own survivors (8 ballots, no block-wide scan or barrier) in (pixel slot, lane) order, so queue
-    // neighbours are tile-row neighbours and the ring loads of step 2 stay (nearly) free of bank conflicts; it then scores
-    // them 32 at a time.
-    const int lane = threadIdx.x, wrp = threadIdx.y;
+    // neighbours are tile-row neighbours; it then scores them 32 at a time.
     uint16_t* queue = hard + wrp * (SC_TW * SC_TH / 8);
     const uint32_t below = (1u << lane) - 1u;
     int nh = 0;
@@ -304,19 +308,23 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     for (int b = 0; b < 8; b++) {
         const uint32_t bal = __ballot_sync(0xffffffffu, (mine >> b) & 1u);
         if ((mine >> b) & 1u)
-            queue[nh + __popc(bal & below)] = (uint16_t)(((threadIdx.y + 8 * (b >> 1)) << 6) | (threadIdx.x + 32 * (b & 1)));
+            queue[nh + __popc(bal & below)] = (uint16_t)(((wrp + 8 * (b >> 1)) << 6) | (2 * lane + (b & 1)));
         nh += __popc(bal);
     }
     __syncwarp();
+    // ---- step 2: full closed-form score of the queued pixels ----
+    const uint16_t* px16 = reinterpret_cast<const uint16_t*>(&E[0][0]);       // E as 16-bit pixels: staged (row, column)
     for (int i = lane; i < nh; i += 32) {
         const int ly = queue[i] >> 6, lx = queue[i] & 63;
-        const uint32_t* c = &tile[ly + 3][lx + 4];
+        const uint16_t* c = px16 + (ly + 3) * SC_SW + lx + 4;
         uint32_t r[16];
-        r[0] = c[-3];                 r[1] = c[-SC_SW - 3];         r[2] = c[-2 * SC_SW - 2];     r[3] = c[-3 * SC_SW - 1];
-        r[4] = c[-3 * SC_SW];         r[5] = c[-3 * SC_SW + 1];     r[6] = c[-2 * SC_SW + 2];     r[7] = c[-SC_SW + 3];
-        r[8] = c[3];                  r[9] = c[SC_SW + 3];          r[10] = c[2 * SC_SW + 2];     r[11] = c[3 * SC_SW + 1];
-        r[12] = c[3 * SC_SW];         r[13] = c[3 * SC_SW - 1];     r[14] = c[2 * SC_SW - 2];     r[15] = c[SC_SW - 3];
-        const int sc = oast_score_packed(r, c[0]);
+#define MFK_W(v) (0x00ff0000u - (uint32_t)(v) * 65535u)                       /* v | (255 - v) << 16 */
+        r[0] = MFK_W(c[-3]);                 r[1] = MFK_W(c[-SC_SW - 3]);         r[2] = MFK_W(c[-2 * SC_SW - 2]);     r[3] = MFK_W(c[-3 * SC_SW - 1]);
+        r[4] = MFK_W(c[-3 * SC_SW]);         r[5] = MFK_W(c[-3 * SC_SW + 1]);     r[6] = MFK_W(c[-2 * SC_SW + 2]);     r[7] = MFK_W(c[-SC_SW + 3]);
+        r[8] = MFK_W(c[3]);                  r[9] = MFK_W(c[SC_SW + 3]);          r[10] = MFK_W(c[2 * SC_SW + 2]);     r[11] = MFK_W(c[3 * SC_SW + 1]);
+        r[12] = MFK_W(c[3 * SC_SW]);         r[13] = MFK_W(c[3 * SC_SW - 1]);     r[14] = MFK_W(c[2 * SC_SW - 2]);     r[15] = MFK_W(c[SC_SW - 3]);
+        const int sc = oast_score_packed(r, MFK_W(c[0]));
+#undef MFK_W
         score_tile[ly][lx] = (uint8_t)sc;
         if (sc >= BRISK_THRESHOLD) atomicOr(reinterpret_cast<unsigned*>(&row_hits[ly]) + (lx >> 5), 1u << (lx & 31));   // native 32-bit shared atomic
     }

@@ -28,6 +28,9 @@ static inline uint32_t __vimax3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
     return lo | (hi << 16);
 }
 
+static inline uint32_t __vmaxu2(uint32_t a, uint32_t b) { return __vimax3_u16x2(a, b, b); }
+static inline uint32_t __vminu2(uint32_t a, uint32_t b) { return __vimin3_u16x2(a, b, b); }
+
 #include "../mofreak_b200/csrc/dense_device.cuh"
 #include "../mofreak_b200/csrc/sparse_device.cuh"
 #include "../mofreak_b200/csrc/desc_device.cuh"
@@ -93,7 +96,20 @@ struct Harness {
                         for (int i = 0; i < 16; i++) { const uint32_t v = im[(y + RY[i]) * L.w + x + RX[i]]; r[i] = v | ((255u - v) << 16); }
                         const uint32_t v = im[y * L.w + x];
                         s = oast_score_packed(r, v | ((255u - v) << 16));
-                        if (oast_score_bound_packed(r, v | ((255u - v) << 16)) <= 0 && s != 0) abort();   // the bound must be sound
+                        const int bound = oast_score_bound_packed(r, v | ((255u - v) << 16));
+                        if (bound <= 0 && s != 0) abort();                                                   // the bound must be sound
+                        if (x + 1 < L.w - 3) {
+                            // the two-centres-per-word form k_scores runs: each half must equal the single-centre bound (+ 256)
+                            uint32_t rp[16];
+                            for (int i = 0; i < 16; i++)
+                                rp[i] = (uint32_t)im[(y + RY[i]) * L.w + x + RX[i]] | ((uint32_t)im[(y + RY[i]) * L.w + x + 1 + RX[i]] << 16);
+                            const uint32_t both = oast_bound_pair(rp, v | ((uint32_t)im[y * L.w + x + 1] << 16));
+                            uint32_t r2[16];
+                            for (int i = 0; i < 16; i++) { const uint32_t u = im[(y + RY[i]) * L.w + x + 1 + RX[i]]; r2[i] = u | ((255u - u) << 16); }
+                            const uint32_t v2 = im[y * L.w + x + 1];
+                            const int bound2 = oast_score_bound_packed(r2, v2 | ((255u - v2) << 16));
+                            if ((int)(both & 0xffffu) != bound + 256 || (int)(both >> 16) != bound2 + 256) abort();
+                        }
                     }
                     S[L.base + y * L.w + x] = (uint8_t)s;
                     if (s >= BRISK_THRESHOLD) { xy.push_back((uint32_t)x | ((uint32_t)y << 16)); meta.push_back((uint32_t)l); row_count[L.row0 + y]++; }

@@ -287,9 +287,9 @@ def test_serial_and_pipelined_launch_sequences_agree(orc):
 
 def test_wide_frames_take_the_separate_dense_kernels(orc):
     """Frames wider than the fused front kernel's band buffer (2048 px) run absdiff / pyramid / row sums as separate kernels."""
-    clip = mofreak_b200.synth_clip(2064, 64, 7, 9)
+    clip = mofreak_b200.synth_clip(2064, 96, 7, 9)
     want = orc.extract_clip(clip)
-    with mofreak_b200.Context(2064, 64, 8, 2) as ctx:
+    with mofreak_b200.Context(2064, 96, 8, 2) as ctx:
         ctx.profile_enable(True)
         got = ctx.extract_clip(clip)
         prof = ctx.profile_read()
@@ -352,7 +352,7 @@ def test_profile_timeline_lists_every_launcher_call_in_stream_order():
         assert all(0.0 <= a <= b <= ms + 1e-3 for _, a, b in tl)
         # within one launch sequence the families follow the dependency order
         first = names[:names.index("describe") + 1]
-        assert first.index("absdiff") < first.index("scores") < first.index("phase_a") < first.index("phase_b") < first.index("describe")
+        assert first.index("front") < first.index("scores") < first.index("phase_a") < first.index("phase_b") < first.index("describe")
         prof = ctx.profile_read()
         assert ctx.profile_timeline() == []                        # consumed by profile_read
         assert prof["scores"][0] == 4
