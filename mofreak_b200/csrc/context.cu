@@ -49,7 +49,7 @@ struct mfk_ctx {
     cudaStream_t copy_stream = nullptr;   // frame-ring uploads, so that H2D of the next frames overlaps the kernels of these
     cudaEvent_t upload_done = nullptr;
     bool upload_pending = false;
-    enum { MAX_LANES = 4 };
+    enum { MAX_LANES = 8 };
     // slots a queued launch sequence still reads, as a few [lo, hi] intervals (frame rings: one interval per stream), so that
     // an upload only waits for the kernels that really read the slots it overwrites
     struct ReadRec {

@@ -39,19 +39,37 @@ __device__ __forceinline__ void roi_stage(WarpScratch& ws, const uint8_t* __rest
                                           int W, int tl_x, int tl_y, int s, int lane, bool async) {
     const int ax = tl_x & ~3;
     const int nw = ((tl_x & 3) + s + 3) >> 2;                       // words per row, <= 9
+    // four rows per pass: lane = (row within the pass) * 8 + word, so that the lanes of a row read neighbouring words;
+    // a ninth word (only for sides >= 30 at an odd offset) takes one extra pass with a lane per row
+    const int rl = lane >> 3, k = lane & 7;
     const size_t org = (size_t)tl_y * W + ax;
-    for (int i = lane; i < s * ROI_WORDS; i += 32) {
-        const int r = i / ROI_WORDS, k = i - r * ROI_WORDS;
-        if (k >= nw) continue;
-        const size_t off = org + (size_t)r * W + 4 * k;
-        uint8_t* d0 = &ws.roi[0][r * ROI_STRIDE + 4 * k];
-        uint8_t* d1 = &ws.roi[1][r * ROI_STRIDE + 4 * k];
+    const uint8_t* c = cur + org + (size_t)rl * W + 4 * k;
+    const uint8_t* p = prev + org + (size_t)rl * W + 4 * k;
+    uint8_t* s0 = &ws.roi[0][rl * ROI_STRIDE + 4 * k];
+    uint8_t* s1 = &ws.roi[1][rl * ROI_STRIDE + 4 * k];
+    const bool col = k < nw;
+    for (int r = rl; r < s; r += 4) {
+        if (col) {
+            if (async) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(s0)), "l"(c) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(s1)), "l"(p) : "memory");
+            } else {
+                *reinterpret_cast<uint32_t*>(s0) = load4(c);
+                *reinterpret_cast<uint32_t*>(s1) = load4(p);
+            }
+        }
+        c += (size_t)4 * W; p += (size_t)4 * W; s0 += 4 * ROI_STRIDE; s1 += 4 * ROI_STRIDE;
+    }
+    if (nw == 9 && lane < s) {
+        const size_t off = org + (size_t)lane * W + 32;
+        uint8_t* e0 = &ws.roi[0][lane * ROI_STRIDE + 32];
+        uint8_t* e1 = &ws.roi[1][lane * ROI_STRIDE + 32];
         if (async) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(d0)), "l"(cur + off));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(d1)), "l"(prev + off));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(e0)), "l"(cur + off));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(e1)), "l"(prev + off));
         } else {
-            *reinterpret_cast<uint32_t*>(d0) = load4(cur + off);
-            *reinterpret_cast<uint32_t*>(d1) = load4(prev + off);
+            *reinterpret_cast<uint32_t*>(e0) = load4(cur + off);
+            *reinterpret_cast<uint32_t*>(e1) = load4(prev + off);
         }
     }
     if (async) asm volatile("cp.async.commit_group;");
@@ -110,7 +128,7 @@ __device__ __forceinline__ void mip_bits(const WarpScratch& ws, int lane, uint32
 
 }  // namespace
 
-__global__ void __launch_bounds__(DW * 32)
+__global__ void __launch_bounds__(DW * 32, 6)       // 6 blocks per SM (40 registers): the kernel waits on gathers, occupancy pays
 k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, int store_frames, PairList pl,
            const int32_t* __restrict__ integral, CandBuf cb, DeviceTables tb, RowOut* __restrict__ rows) {
     __shared__ WarpScratch scratch[DW];
@@ -155,8 +173,8 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
             d0 += delta * op.wdx / 2048;
             d1 += delta * op.wdy / 2048;
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+        d0 = __reduce_add_sync(0xffffffffu, d0);                       // REDUX: one instruction per warp sum
+        d1 = __reduce_add_sync(0xffffffffu, d1);
         const int theta = freak_theta_index(d0, d1);
 
         // --- FREAK: the 64 pair tests the reference keeps ---

@@ -23,8 +23,12 @@ constexpr int FR_BAND = 12;
 constexpr int FR_THREADS = 256;
 constexpr int FR_MAX_W = 2048;            // wider frames take the separate kernels (shared memory per band)
 constexpr int IG_STRIP_W = 128;           // strip width of k_integral_strips (kernels_dense.cu)
+constexpr int FR_BAND_PX = 8640;          // pixels of layer 0 a block should own (12 rows of 720)
+constexpr int FR_MULT_MAX = 8;
+constexpr int FR_SUMS = 256;              // (rows, strip) sums of one band: rows * ceil(W / 128) <= 12 * mult * (W / 128 + 1)
 
 struct FrontLayout {                      // shared-memory plan of one band
+    int mult;                             // a band is 12 * mult source rows: narrow frames take taller bands, so that a block has ~8K pixels
     int pitch[N_LAYERS];                  // row pitch of each layer's band, a multiple of 16
     int off[N_LAYERS];                    // byte offsets: layer 0 = current frame (becomes the difference), then layers 1..5
     int off_prev;                         // previous frame's band
@@ -77,34 +81,78 @@ __device__ __forceinline__ void half_band(const uint8_t* __restrict__ src, int s
     }
 }
 
-// BriskLayer::twothirdsample on `groups` row triples of a shared band: one 3x3 source block -> 2x2 outputs per thread
+// one 3x3 source block -> its 2x2 outputs (the per-triple form of BriskLayer::twothirdsample)
+__device__ __forceinline__ void twothird_triple(const uint8_t* __restrict__ r1, int sp, uint8_t* __restrict__ d1, int dp, bool in_block, bool fifth) {
+    const uint8_t* r2 = r1 + sp;
+    const uint8_t* r3 = r2 + sp;
+    uint8_t* d2 = d1 + dp;
+    const int a0 = r1[0], a1 = r1[1], a2 = r1[2], b0 = r2[0], b1 = r2[1], b2 = r2[2], c0 = r3[0], c1 = r3[1], c2 = r3[2];
+    if (in_block) {
+        // inside a 15-column block: avg(avg(a,b),a) chains, vertically then horizontally; the fifth triple takes its
+        // middle sample from the block's byte 12, i.e. from its own first column (brisk.cpp:1982-1983)
+        const int u0 = avg_up(avg_up(a0, b0), a0), u2 = avg_up(avg_up(a2, b2), a2);
+        const int l0 = avg_up(avg_up(c0, b0), c0), l2 = avg_up(avg_up(c2, b2), c2);
+        const int um = fifth ? u0 : avg_up(avg_up(a1, b1), a1);
+        const int lm = fifth ? l0 : avg_up(avg_up(c1, b1), c1);
+        d1[0] = (uint8_t)avg_up(avg_up(u0, um), u0); d1[1] = (uint8_t)avg_up(avg_up(u2, um), u2);
+        d2[0] = (uint8_t)avg_up(avg_up(l0, lm), l0); d2[1] = (uint8_t)avg_up(avg_up(l2, lm), l2);
+    } else {
+        // trailing triples: (4A + 2(B+C) + D) / 9 (brisk.cpp:2036-2051)
+        d1[0] = (uint8_t)((4 * a0 + 2 * (a1 + b0) + b1) / 9); d1[1] = (uint8_t)((4 * a2 + 2 * (a1 + b2) + b1) / 9);
+        d2[0] = (uint8_t)((4 * c0 + 2 * (c1 + b0) + b1) / 9); d2[1] = (uint8_t)((4 * c2 + 2 * (c1 + b2) + b1) / 9);
+    }
+}
+
+// horizontal pass of four triples at once: L, M, R hold the left, middle and right column of each triple (one byte per
+// triple); returns the eight outputs in order
+__device__ __forceinline__ uint2 twothird_horizontal4(uint32_t L, uint32_t M, uint32_t R) {
+    const uint32_t ol = __vavgu4(__vavgu4(L, M), L), orr = __vavgu4(__vavgu4(R, M), R);
+    return make_uint2(__byte_perm(ol, orr, 0x5140), __byte_perm(ol, orr, 0x7362));
+}
+
+// BriskLayer::twothirdsample on `groups` row triples of a shared band.  A thread takes FOUR column triples of one row
+// triple: 12 source bytes per row are three aligned words, the avg(avg(a,b),a) chains run on packed bytes (the SSE
+// code's own formulation, _mm_avg_epu8), byte permutes gather each triple's left / middle / right column; triples of the
+// trailing rule and a last incomplete quad take the per-triple form.
 __device__ __forceinline__ void twothird_band(const uint8_t* __restrict__ src, int sp, int sw, uint8_t* __restrict__ dst, int dp, int dw,
                                               int groups, int tid) {
     if (groups <= 0) return;
     const int triples = dw >> 1;
-    const int blocks = sw / 15;
-    for (int i = tid; i < groups * triples; i += FR_THREADS) {
-        const int gt = i / triples, tc = i - gt * triples;
-        const uint8_t* r1 = src + (3 * gt) * sp + 3 * tc;
-        const uint8_t* r2 = r1 + sp;
-        const uint8_t* r3 = r2 + sp;
-        uint8_t* d1 = dst + (2 * gt) * dp + 2 * tc;
-        uint8_t* d2 = d1 + dp;
-        const int a0 = r1[0], a1 = r1[1], a2 = r1[2], b0 = r2[0], b1 = r2[1], b2 = r2[2], c0 = r3[0], c1 = r3[1], c2 = r3[2];
-        if (tc < 5 * blocks) {
-            // inside a 15-column block: avg(avg(a,b),a) chains, vertically then horizontally; the fifth triple takes its
-            // middle sample from the block's byte 12, i.e. from its own first column (brisk.cpp:1982-1983)
-            const bool fifth = (tc % 5) == 4;
-            const int u0 = avg_up(avg_up(a0, b0), a0), u2 = avg_up(avg_up(a2, b2), a2);
-            const int l0 = avg_up(avg_up(c0, b0), c0), l2 = avg_up(avg_up(c2, b2), c2);
-            const int um = fifth ? u0 : avg_up(avg_up(a1, b1), a1);
-            const int lm = fifth ? l0 : avg_up(avg_up(c1, b1), c1);
-            d1[0] = (uint8_t)avg_up(avg_up(u0, um), u0); d1[1] = (uint8_t)avg_up(avg_up(u2, um), u2);
-            d2[0] = (uint8_t)avg_up(avg_up(l0, lm), l0); d2[1] = (uint8_t)avg_up(avg_up(l2, lm), l2);
+    const int in_blocks = 5 * (sw / 15);                   // triples that follow the block rule
+    const int quads = (triples + 3) >> 2;
+    for (int i = tid; i < groups * quads; i += FR_THREADS) {
+        const int gt = i / quads, q = i - gt * quads;
+        const uint8_t* r1 = src + (3 * gt) * sp + 12 * q;
+        uint8_t* d1 = dst + (2 * gt) * dp + 8 * q;
+        if (4 * q + 4 <= in_blocks) {
+            const uint32_t* a = reinterpret_cast<const uint32_t*>(r1);
+            const uint32_t* b = reinterpret_cast<const uint32_t*>(r1 + sp);
+            const uint32_t* c = reinterpret_cast<const uint32_t*>(r1 + 2 * sp);
+            uint32_t U[3], D[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const uint32_t av = a[k], bv = b[k], cv = c[k];
+                U[k] = __vavgu4(__vavgu4(av, bv), av);
+                D[k] = __vavgu4(__vavgu4(cv, bv), cv);
+            }
+            // the triple whose index is 4 (mod 5) is the fifth of its 15-column block: its middle column is its left one
+            const int kk = (4 + q) % 5;
+            const uint32_t fifth = kk < 4 ? 0xffu << (8 * kk) : 0u;
+            uint32_t L = __byte_perm(__byte_perm(U[0], U[1], 0x0630), U[2], 0x5210);
+            uint32_t M = __byte_perm(__byte_perm(U[0], U[1], 0x0741), U[2], 0x6210);
+            uint32_t R = __byte_perm(__byte_perm(U[0], U[1], 0x0052), U[2], 0x7410);
+            M = (M & ~fifth) | (L & fifth);
+            *reinterpret_cast<uint2*>(d1) = twothird_horizontal4(L, M, R);
+            L = __byte_perm(__byte_perm(D[0], D[1], 0x0630), D[2], 0x5210);
+            M = __byte_perm(__byte_perm(D[0], D[1], 0x0741), D[2], 0x6210);
+            R = __byte_perm(__byte_perm(D[0], D[1], 0x0052), D[2], 0x7410);
+            M = (M & ~fifth) | (L & fifth);
+            *reinterpret_cast<uint2*>(d1 + dp) = twothird_horizontal4(L, M, R);
         } else {
-            // trailing triples: (4A + 2(B+C) + D) / 9 (brisk.cpp:2036-2051)
-            d1[0] = (uint8_t)((4 * a0 + 2 * (a1 + b0) + b1) / 9); d1[1] = (uint8_t)((4 * a2 + 2 * (a1 + b2) + b1) / 9);
-            d2[0] = (uint8_t)((4 * c0 + 2 * (c1 + b0) + b1) / 9); d2[1] = (uint8_t)((4 * c2 + 2 * (c1 + b2) + b1) / 9);
+            for (int k = 0; k < 4 && 4 * q + k < triples; k++) {
+                const int tc = 4 * q + k;
+                twothird_triple(r1 + 3 * k, sp, d1 + 2 * k, dp, tc < in_blocks, (tc % 5) == 4);
+            }
         }
     }
 }
@@ -115,9 +163,11 @@ k_front(const __grid_constant__ Geom g, const __grid_constant__ FrontLayout fl, 
         PairList pl, uint8_t* __restrict__ img_all, int32_t* __restrict__ left, int strips) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ int strip_sum[FR_SUMS];
     const int band = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const int W = g.W, H = g.H;
-    const int y0 = band * FR_BAND, rows = min(FR_BAND, H - y0);
+    const int m = fl.mult;
+    const int y0 = band * FR_BAND * m, rows = min(FR_BAND * m, H - y0);
     uint8_t* A = sm + fl.off[0];
     uint8_t* B = sm + fl.off_prev;
     const int p0 = fl.pitch[0];
@@ -159,44 +209,44 @@ k_front(const __grid_constant__ Geom g, const __grid_constant__ FrontLayout fl, 
     // ---- layer 0 out, its row strip sums, layers 1 and 2 into shared memory ----
     copy_out(img_all + g.L[0].base + (size_t)f * g.L[0].px + (size_t)y0 * W, A, p0, W, rows, tid);
     {
-        // left[y][s] = sum of the row's pixels left of 128-column strip s (what k_integral_strips starts each row from)
+        // sums of the 128-column strips of every row (a warp per (row, strip): one word per lane, one REDUX); the prefix over
+        // the strips of a row - left[y][s], what k_integral_strips starts each row from - follows after the next barrier
         const int lane = tid & 31;
-        for (int r = tid >> 5; r < rows; r += FR_THREADS / 32) {
-            int32_t* out = left + ((size_t)f * H + y0 + r) * strips;
-            int carry = 0;
-            for (int s = 0; s < strips; s++) {
-                const int x = s * IG_STRIP_W + 4 * lane;
-                uint32_t v = 0;
-                if (x < W) {
-                    v = *reinterpret_cast<const uint32_t*>(A + r * p0 + x);
-                    if (x + 4 > W) v &= (1u << (8 * (W - x))) - 1u;
-                }
-                int sum = (int)__dp4a(v, 0x01010101u, 0u);
-#pragma unroll
-                for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-                if (lane == 0) out[s] = carry;
-                carry += sum;
+        for (int u = tid >> 5; u < rows * strips; u += FR_THREADS / 32) {
+            const int r = u / strips, sidx = u - r * strips;
+            const int x = sidx * IG_STRIP_W + 4 * lane;
+            uint32_t v = 0;
+            if (x < W) {
+                v = *reinterpret_cast<const uint32_t*>(A + r * p0 + x);
+                if (x + 4 > W) v &= (1u << (8 * (W - x))) - 1u;
             }
+            const int sum = __reduce_add_sync(0xffffffffu, (int)__dp4a(v, 0x01010101u, 0u));
+            if (lane == 0) strip_sum[u] = sum;
         }
     }
     uint8_t* S1 = sm + fl.off[1]; uint8_t* S2 = sm + fl.off[2]; uint8_t* S3 = sm + fl.off[3];
     uint8_t* S4 = sm + fl.off[4]; uint8_t* S5 = sm + fl.off[5];
     // rows of each layer this band produces (the layers' heights are not multiples of the band's share in general)
-    const int n1 = min(8, g.L[1].h - 8 * band), n2 = min(6, g.L[2].h - 6 * band), n3 = min(4, g.L[3].h - 4 * band);
-    const int n4 = min(3, g.L[4].h - 3 * band), n5 = min(2, g.L[5].h - 2 * band);
+    const int n1 = min(8 * m, g.L[1].h - 8 * m * band), n2 = min(6 * m, g.L[2].h - 6 * m * band), n3 = min(4 * m, g.L[3].h - 4 * m * band);
+    const int n4 = min(3 * m, g.L[4].h - 3 * m * band), n5 = min(2 * m, g.L[5].h - 2 * m * band);
     twothird_band(A, p0, W, S1, fl.pitch[1], g.L[1].w, n1 > 0 ? n1 / 2 : 0, tid);
     half_band(A, p0, W, S2, fl.pitch[2], g.L[2].w, n2, tid);
     __syncthreads();
-    copy_out(img_all + g.L[1].base + (size_t)f * g.L[1].px + (size_t)(8 * band) * g.L[1].w, S1, fl.pitch[1], g.L[1].w, n1, tid);
-    copy_out(img_all + g.L[2].base + (size_t)f * g.L[2].px + (size_t)(6 * band) * g.L[2].w, S2, fl.pitch[2], g.L[2].w, n2, tid);
+    if (tid < rows) {
+        int32_t* out = left + ((size_t)f * H + y0 + tid) * strips;
+        int carry = 0;
+        for (int sidx = 0; sidx < strips; sidx++) { out[sidx] = carry; carry += strip_sum[tid * strips + sidx]; }
+    }
+    copy_out(img_all + g.L[1].base + (size_t)f * g.L[1].px + (size_t)(8 * m * band) * g.L[1].w, S1, fl.pitch[1], g.L[1].w, n1, tid);
+    copy_out(img_all + g.L[2].base + (size_t)f * g.L[2].px + (size_t)(6 * m * band) * g.L[2].w, S2, fl.pitch[2], g.L[2].w, n2, tid);
     half_band(S1, fl.pitch[1], g.L[1].w, S3, fl.pitch[3], g.L[3].w, n3, tid);
     half_band(S2, fl.pitch[2], g.L[2].w, S4, fl.pitch[4], g.L[4].w, n4, tid);
     __syncthreads();
-    copy_out(img_all + g.L[3].base + (size_t)f * g.L[3].px + (size_t)(4 * band) * g.L[3].w, S3, fl.pitch[3], g.L[3].w, n3, tid);
-    copy_out(img_all + g.L[4].base + (size_t)f * g.L[4].px + (size_t)(3 * band) * g.L[4].w, S4, fl.pitch[4], g.L[4].w, n4, tid);
+    copy_out(img_all + g.L[3].base + (size_t)f * g.L[3].px + (size_t)(4 * m * band) * g.L[3].w, S3, fl.pitch[3], g.L[3].w, n3, tid);
+    copy_out(img_all + g.L[4].base + (size_t)f * g.L[4].px + (size_t)(3 * m * band) * g.L[4].w, S4, fl.pitch[4], g.L[4].w, n4, tid);
     half_band(S3, fl.pitch[3], g.L[3].w, S5, fl.pitch[5], g.L[5].w, n5, tid);
     __syncthreads();
-    copy_out(img_all + g.L[5].base + (size_t)f * g.L[5].px + (size_t)(2 * band) * g.L[5].w, S5, fl.pitch[5], g.L[5].w, n5, tid);
+    copy_out(img_all + g.L[5].base + (size_t)f * g.L[5].px + (size_t)(2 * m * band) * g.L[5].w, S5, fl.pitch[5], g.L[5].w, n5, tid);
 }
 
 }  // namespace
@@ -206,16 +256,22 @@ bool front_supported(const Geom& g) { return g.W <= FR_MAX_W; }
 cudaError_t launch_front(cudaStream_t st, const Geom& g, const uint8_t* store, int store_frames, PairList pl, uint8_t* img, int32_t* left) {
     FrontLayout fl;
     static const int band_rows[N_LAYERS] = {12, 8, 6, 4, 3, 2};
+    const int strips = (g.W + IG_STRIP_W - 1) / IG_STRIP_W;
+    // taller bands for narrow frames (a 12-row band of a 160-pixel frame is 1920 pixels: all overhead), bounded by the strip-sum
+    // scratch and the frame height
+    int mult = FR_BAND_PX / (FR_BAND * g.W);
+    mult = mult < 1 ? 1 : (mult > FR_MULT_MAX ? FR_MULT_MAX : mult);
+    while (mult > 1 && (FR_BAND * mult * strips > FR_SUMS || FR_BAND * (mult - 1) >= g.H)) mult--;
+    fl.mult = mult;
     int at = 0;
     for (int l = 0; l < N_LAYERS; l++) {
         fl.pitch[l] = (g.L[l].w + 15) & ~15;
         fl.off[l] = at;
-        at += band_rows[l] * fl.pitch[l];
-        if (l == 0) { fl.off_prev = at; at += band_rows[0] * fl.pitch[0]; }
+        at += band_rows[l] * mult * fl.pitch[l];
+        if (l == 0) { fl.off_prev = at; at += band_rows[0] * mult * fl.pitch[0]; }
     }
     fl.total = at;
-    const int strips = (g.W + IG_STRIP_W - 1) / IG_STRIP_W;
-    const dim3 grid((g.H + FR_BAND - 1) / FR_BAND, g.F);
+    const dim3 grid((g.H + FR_BAND * mult - 1) / (FR_BAND * mult), g.F);
     const bool tma = (g.W & 15) == 0;            // slots, bands and rows then start 16-byte aligned and a band is a multiple of 16 bytes
     cudaError_t e;
     if (tma) {

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
             again = more;
             group_sync<G>(grp);
         } while (again);
-        __threadfence();        // seen marks of layer li+1 are complete before its ties are examined
+        __threadfence_block();  // this group wrote the seen marks of layer li+1 that matter to it (phase A's are complete since its kernels ended)
         group_sync<G>(grp);
     }
 }

@@ -19,8 +19,9 @@ ctx = mofreak_b200.Context(W, H, STREAMS * FPS, len(cur))
 ctx.set_serial(True)
 ctx.upload_frames(clip)
 ctx.bow_set_codebook(np.random.default_rng(7).integers(0, 256, (600, 16), dtype=np.uint8))
-kps = np.stack([np.random.default_rng(1).uniform(80, W - 80, 4096), np.random.default_rng(2).uniform(80, H - 80, 4096),
-                np.random.default_rng(3).uniform(8.4, 60, 4096)], 1).astype(np.float32)
+margin = min(80, W // 3, H // 3)
+kps = np.stack([np.random.default_rng(1).uniform(margin, W - margin, 4096), np.random.default_rng(2).uniform(margin, H - margin, 4096),
+                np.random.default_rng(3).uniform(8.4, min(60, margin), 4096)], 1).astype(np.float32)
 for it in range(iters):
     before = ctx.launch_count()
     ctx.reset_rows()

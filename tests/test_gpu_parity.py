@@ -51,6 +51,57 @@ def test_rows_equal_oracle(orc, shape, frames, seed):
     assert util.rows_equal(got, want), util.describe_diff(got, want)
 
 
+def blob_clip(w, h, n, seed, zoom=16, step=3, mix=0.5):
+    """Smooth large-scale structure (a random pattern upsampled `zoom` x with cubic interpolation, drifting `step` px per frame)
+    mixed with the moving-squares clip: its difference images have corners at EVERY pyramid scale, so keypoints of all six
+    layers, large FREAK patterns and MIP regions wider than the staged 32 px occur in numbers."""
+    from scipy import ndimage
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (h // zoom + 8, w // zoom + 8)).astype(np.float64)
+    big = np.clip(ndimage.zoom(base, zoom, order=3), 0, 255)
+    fine = mofreak_b200.synth_clip(w, h, n, seed).astype(np.float64)
+    out = np.empty((n, h, w), np.uint8)
+    for t in range(n):
+        o = step * t
+        out[t] = np.clip(mix * big[o:o + h, o:o + w] + (1 - mix) * fine[t], 0, 255).astype(np.uint8)
+    return out
+
+
+def coverage(orc, clip):
+    """What a clip exercises, from the oracle's side: keypoints per pyramid layer, FREAK scale indices of the rows, MIP region
+    sides on either side of the kernel's staging limit (kernels_desc.cu ROI_MAX = 32), orientation bins."""
+    layers = np.zeros(6, int)
+    sidx, thetas, staged, unstaged = set(), set(), 0, 0
+    for _, d in util.diff_frames(clip):
+        kps = orc.brisk(d)
+        layers += np.bincount(kps[:, 4].astype(int), minlength=6)
+        kept, _, theta = orc.freak_compute(d, kps)
+        sidx |= {orc.freak_scale_index(float(sz)) for sz in kept[:, 2]}
+        thetas |= set(theta.tolist())
+        sides = np.ceil(kept[:, 2])
+        staged += int((sides <= 32).sum()); unstaged += int((sides > 32).sum())
+    return layers, sidx, thetas, staged, unstaged
+
+
+@pytest.mark.parametrize("shape,seed,blobs", [((720, 576), 13, False), ((1280, 720), 17, False), ((720, 576), 5, True), ((366, 250), 6, True)])
+def test_parity_cases_cover_every_layer_scale_and_mip_path(orc, shape, seed, blobs):
+    """Rows equal the oracle's AND the inputs are known to exercise the paths: every pyramid layer emits keypoints, the
+    FREAK scale index takes >= 20 distinct values, MIP regions are staged (side <= 32) and unstaged (> 32), and for widths
+    that are not a multiple of 4 the synchronous (non-cp.async) staging path runs."""
+    w, h = shape
+    clip = blob_clip(w, h, 7, seed) if blobs else mofreak_b200.synth_clip(w, h, 7, seed)
+    layers, sidx, thetas, staged, unstaged = coverage(orc, clip)
+    assert (layers > 0).all(), "keypoints per layer %s" % layers
+    assert len(sidx) >= 20 and len(thetas) >= 64
+    assert staged > 0 and unstaged > 0
+    if blobs:
+        assert layers[3:].sum() > layers.sum() // 4          # the upper layers carry a large share here
+        assert unstaged >= (100 if w >= 720 else 5)
+    got = run_clip(clip)
+    want = orc.extract_clip(clip)
+    assert len(want) > 100 and util.rows_equal(got, want), util.describe_diff(got, want)
+
+
 def test_stages_equal_oracle(orc):
     w, h, n = 212, 163, 8
     clip = mofreak_b200.synth_clip(w, h, n, 21)

@@ -236,3 +236,58 @@ def test_command_line_cluster_stage(tmp_path):
     assert len(lines) == 10 and all(len(l.split()) == 16 and l.endswith(" ") for l in lines)
     subprocess.run(args, capture_output=True, text=True, check=True)
     assert (tmp_path / "clusters.txt").read_text() == first                      # seeded: reproducible
+
+
+@pytest.mark.gpu
+def test_detection_to_classification_pipeline_files(orc, tmp_path):
+    """BASELINE configs[4] up to the SVM (main.cpp:944-962: computeMoFREAKFiles -> cluster -> computeBOWRepresentation) on a
+    6-clip 320x240 synthetic set, through the command-line driver; every file it writes is compared byte for byte with what
+    the oracle pipeline produces: `.mofreak` (extraction), clusters.txt (seeded codebook selection; cluster_restate.cpp fed
+    with the generator's numbers), <k>.train / <k>.test (loadClusters quirk, histograms, leave-one-group-out fan-out)."""
+    from tests.test_oracle_next_rows import lcg15
+    exe = os.path.join(HOST_DIR, "mofreak_main")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", HOST_DIR], check=True)
+    names = [("person01_boxing_d1_uncomp", 1), ("person02_boxing_d2_uncomp", 1), ("person03_boxing_d1_uncomp", 1),
+             ("person01_walking_d1_uncomp", 2), ("person02_walking_d3_uncomp", 2), ("person03_walking_d2_uncomp", 2)]
+    K, n_classes, groups, seed = 24, 2, 3, 11
+    args, rows_of = [], {}
+    for i, (nm, cls) in enumerate(names):
+        clip = mofreak_b200.synth_clip(320, 240, 11, 500 + i)
+        video = tmp_path / (nm + ".y8")
+        video.write_bytes(b"MFKGRAY1" + np.array([320, 240, 11], "<i4").tobytes() + clip.tobytes())
+        args.append("%d:%s" % (cls, video))
+        rows_of[nm] = orc.extract_clip(clip)
+        assert len(rows_of[nm]) > K
+    r = subprocess.run([exe, "pipeline", "KTH", str(K), str(n_classes), str(groups), str(tmp_path), str(seed)] + args,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # 1. extraction
+    for nm, _ in names:
+        assert (tmp_path / (nm + ".mofreak")).read_text() == orc.format_mofreak(rows_of[nm])
+    # 2. codebook: per class, files are read in order, each file's rows reversed (the reader), three seeded shuffles
+    centers, center_row, shuffles = np.zeros((K, 16), np.uint8), 0, 0
+    for cls in (1, 2):
+        rows = np.concatenate([rows_of[nm][::-1] for nm, c in names if c == cls])
+        data = np.zeros((len(rows), 19), np.uint8)
+        data[:, 3:11] = rows["appearance"]; data[:, 11:] = rows["motion"]
+        rands = []
+        for _ in range(3):
+            rands += lcg15(seed + 0x9E3779B9 * shuffles, len(rows) - 1); shuffles += 1
+        centers, center_row, _, _ = orc.random_clusters(data, K, n_classes, [1, 2], True, rands, centers, center_row)
+    assert center_row == K
+    text = orc.clusters_text(centers)
+    assert (tmp_path / "clusters.txt").read_text() == text
+    # 3. bag of words with the loader's off-by-one (first line unused, last codeword repeats the last value)
+    loaded = orc.load_clusters(text)
+    assert len(loaded) == K
+    expect, actions = [], {}
+    for nm, _ in names:
+        ok, hist = orc.build_histogram(orc.format_mofreak(rows_of[nm]), loaded)
+        assert ok
+        act = nm.split("_")[1]
+        actions.setdefault(act, len(actions))
+        expect.append((int(nm.split("_")[0][-2:]) - 1, libsvm_line(actions[act] + 1, hist)))
+    for g in range(groups):
+        assert (tmp_path / ("%d.test" % (g + 1))).read_text().splitlines() == [l for (grp, l) in expect if grp == g]
+        assert (tmp_path / ("%d.train" % (g + 1))).read_text().splitlines() == [l for (grp, l) in expect if grp != g]
