@@ -169,21 +169,28 @@ __device__ __forceinline__ void group_sync(int grp) {
     else asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "r"(G) : "memory");
 }
 
+// Shared memory of one block (dynamic: 27 bytes per list slot, PB_LIST slots shared by the block's pairs).  The candidates'
+// coordinates and, for the winners of a round, their own scores travel with the lists, so that a round costs four dependent
+// global-memory round trips (tie window; scan above; scan below; own patch) instead of seven.
 template <int G>
 __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
     constexpr int PER = PB_THREADS / G;          // pairs per block
     constexpr int LIST = PB_LIST / PER;          // list capacity of one pair
-    __shared__ uint32_t list_s[PER][2][LIST];    // undecided tie candidates of this round / of the next round
-    __shared__ uint32_t passed_s[PER][LIST];     // this round's winners, re-packed so that the scans run on full warps
-    __shared__ uint8_t verdict_s[PER][LIST];
+    extern __shared__ __align__(16) uint32_t pb_smem[];
     __shared__ int ctl[PER][4];                  // n_list, n_next, n_pass, more
     __shared__ int warp_cnt[PB_THREADS / 32];
     const int grp = threadIdx.x / G, t = threadIdx.x % G;
     const int f = blockIdx.x * PER + grp;
     if (f >= g.F) return;                        // whole groups leave; every barrier below is per group
-    uint32_t (*list)[LIST] = list_s[grp];
-    uint32_t* passed = passed_s[grp];
-    uint8_t* verdict = verdict_s[grp];
+    // per pair: list[2][LIST] | list_xy[2][LIST] | passed[LIST] | passed_xy[LIST] | verdict[LIST] | center[LIST] | passed_center[LIST]
+    uint32_t* mine = pb_smem + (size_t)grp * (6 * LIST + 3 * LIST / 4);
+    uint32_t (*list)[LIST] = reinterpret_cast<uint32_t (*)[LIST]>(mine);            // undecided tie candidates of this round / of the next
+    uint32_t (*lxy)[LIST] = reinterpret_cast<uint32_t (*)[LIST]>(mine + 2 * LIST);  // their x | y << 16
+    uint32_t* passed = mine + 4 * LIST;           // this round's winners, re-packed so that the scans run on full warps
+    uint32_t* passed_xy = mine + 5 * LIST;
+    uint8_t* verdict = reinterpret_cast<uint8_t*>(mine + 6 * LIST);
+    uint8_t* center = verdict + LIST;
+    uint8_t* passed_center = center + LIST;
     volatile int& n_list = ctl[grp][0];
     volatile int& n_next = ctl[grp][1];
     volatile int& n_pass = ctl[grp][2];
@@ -191,13 +198,17 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
     int* const wc = warp_cnt + grp * (G / 32);
     PairView pv; pv.g = &g; pv.m = m; pv.f = f;
     const uint32_t cap = (uint32_t)g.cand_cap;
+    // which layers have tie candidates at all: one load for the six counts instead of a dependent round trip per layer
+    uint32_t pending_of[N_LAYERS];
+#pragma unroll
+    for (int li = 0; li < N_LAYERS; li++) pending_of[li] = cb.pend_count[pv.f * N_LAYERS + li];
     for (int li = 0; li < N_LAYERS; li++) {
+        const uint32_t n_pending = pending_of[li];
+        if (n_pending == 0) continue;
         const LayerGeom& L = g.L[li];
         const size_t r0 = (size_t)pv.f * g.rows + L.row0;
         const uint32_t begin = min(cb.row_count[r0], cap), end = min(cb.row_count[r0 + L.h], cap);
         uint32_t cursor = begin;
-        const uint32_t n_pending = cb.pend_count[pv.f * N_LAYERS + li];
-        if (n_pending == 0) continue;
         const bool listed = n_pending <= (uint32_t)min((int)PEND_CAP, LIST);      // phase A's list holds them all and they fit (order is irrelevant then)
         // candidates are in raster order, so taking the pending ones chunk by chunk keeps every dependency
         // (always raster-earlier) inside the current or an already finished chunk
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
             uint32_t next_cursor = end;
             if (listed) {
                 const uint32_t* src = cb.pend_list + (size_t)(pv.f * N_LAYERS + li) * PEND_CAP;
-                for (uint32_t i = t; i < n_pending; i += G) list[0][i] = src[i];
+                for (uint32_t i = t; i < n_pending; i += G) { const uint32_t c = src[i]; list[0][i] = c; lxy[0][i] = cb.xy[c]; }
                 if (t == 0) n_list = (int)n_pending;
             } else
             // gather up to LIST pending candidates starting at cursor, preserving order
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
                 for (int w = 0; w < G / 32; w++) total += wc[w];
                 const int slot = before + __popc(bal & ((1u << (t & 31)) - 1u));
                 const bool fits = n_list + total <= LIST;
-                if (pend && fits) list[0][slot] = c;
+                if (pend && fits) { list[0][slot] = c; lxy[0][slot] = cb.xy[c]; }
                 group_sync<G>(grp);
                 if (!fits) { next_cursor = base; if (t == 0) more = 1; break; }
                 if (t == 0) n_list += total;
@@ -247,30 +258,25 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
 #endif
                 if (t == 0) { n_next = 0; n_pass = 0; }
                 for (int i = t; i < nl; i += G) {
-                    const uint32_t c = list[cur][i];
-                    const uint32_t xy = cb.xy[c];
-                    const int x = xy & 0xffff, y = xy >> 16;
+                    const uint32_t xy = lxy[cur][i];
                     TieWindow tw;
-                    tw.load(pv, li, x, y);
+                    tw.load(pv, li, xy & 0xffff, xy >> 16);
                     verdict[i] = earlier_pending_nearby(tw) ? 0 : (tie_break(tw) ? 2 : 1);
+                    center[i] = (uint8_t)packed_byte(tw.S[3], 3);
                 }
                 group_sync<G>(grp);
                 for (int i = t; i < nl; i += G) {
-                    const uint32_t c = list[cur][i];
+                    const uint32_t c = list[cur][i], xy = lxy[cur][i];
                     const uint8_t v = verdict[i];
-                    if (v == 0) list[cur ^ 1][atomicAdd(&ctl[grp][1], 1)] = c;          // still waiting (order is irrelevant)
-                    else if (v == 2) passed[atomicAdd(&ctl[grp][2], 1)] = c;
-                    else {
-                        const uint32_t xy = cb.xy[c];
-                        pv.m.status[pv.off(li) + (xy >> 16) * L.w + (xy & 0xffff)] = 0; cb.flags[c] = 0;
-                    }
+                    if (v == 0) { const int k = atomicAdd(&ctl[grp][1], 1); list[cur ^ 1][k] = c; lxy[cur ^ 1][k] = xy; }   // still waiting (order is irrelevant)
+                    else if (v == 2) { const int k = atomicAdd(&ctl[grp][2], 1); passed[k] = c; passed_xy[k] = xy; passed_center[k] = center[i]; }
+                    else { pv.m.status[pv.off(li) + (xy >> 16) * L.w + (xy & 0xffff)] = 0; cb.flags[c] = 0; }
                 }
                 group_sync<G>(grp);
                 const int np = n_pass;
                 for (int i = t; i < np; i += G) {
-                    const uint32_t c = passed[i];
-                    const uint32_t xy = cb.xy[c];
-                    after_max2d(pv, cb, tb, li, xy & 0xffff, xy >> 16, c);
+                    const uint32_t xy = passed_xy[i];
+                    after_max2d(pv, cb, tb, li, xy & 0xffff, xy >> 16, passed[i], passed_center[i]);
                 }
                 __threadfence_block();
                 group_sync<G>(grp);
@@ -299,12 +305,20 @@ int phase_b_group(const Geom& g) {
     return ties <= 400 ? 32 : 64;
 }
 
+template <int G>
+static void launch_phase_b_g(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTables tb) {
+    constexpr int PER = PB_THREADS / G;
+    const size_t smem = (size_t)PB_LIST * 27;                              // 6 words + 3 bytes per list slot
+    cudaFuncSetAttribute(k_phase_b<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     // per device: set on every launch
+    k_phase_b<G><<<(g.F + PER - 1) / PER, PB_THREADS, smem, st>>>(g, m, cb, tb);
+}
+
 void launch_phase_b(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTables tb) {
     switch (phase_b_group(g)) {
-        case 32:  k_phase_b<32><<<(g.F + 7) / 8, PB_THREADS, 0, st>>>(g, m, cb, tb); break;
-        case 64:  k_phase_b<64><<<(g.F + 3) / 4, PB_THREADS, 0, st>>>(g, m, cb, tb); break;
-        case 128: k_phase_b<128><<<(g.F + 1) / 2, PB_THREADS, 0, st>>>(g, m, cb, tb); break;
-        default:  k_phase_b<256><<<g.F, PB_THREADS, 0, st>>>(g, m, cb, tb); break;
+        case 32:  launch_phase_b_g<32>(st, g, m, cb, tb); break;
+        case 64:  launch_phase_b_g<64>(st, g, m, cb, tb); break;
+        case 128: launch_phase_b_g<128>(st, g, m, cb, tb); break;
+        default:  launch_phase_b_g<256>(st, g, m, cb, tb); break;
     }
 }
 

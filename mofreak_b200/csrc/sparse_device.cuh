@@ -45,11 +45,12 @@ __device__ __forceinline__ void finish_failed(const PairView& pv, const CandBuf&
 }
 
 // returns false when a larger score exists above (the candidate is then final)
-__device__ inline bool stage_above(const PairView& pv, const CandBuf& cb, int li, int x, int y, uint32_t c, Scan& up) {
+// (center: the candidate's own score when the caller already holds it, else -1 = read it here)
+__device__ inline bool stage_above(const PairView& pv, const CandBuf& cb, int li, int x, int y, uint32_t c, Scan& up, int center = -1) {
     up = neutral_scan();
     if (li == N_LAYERS - 1) return true;
     const Geom& g = *pv.g;
-    const int center = pv.m.S[pv.off(li) + y * g.L[li].w + x];
+    if (center < 0) center = pv.m.S[pv.off(li) + y * g.L[li].w + x];
     const Footprint fa = scan_footprint(false, li, x, y);
     Window4 wa;
     wa.load(pv.m.S + pv.off(li + 1), g.L[li + 1].w, g.L[li + 1].h, window_origin(fa.x_1, fa.x1), window_origin(fa.y_1, fa.y1));
@@ -60,11 +61,11 @@ __device__ inline bool stage_above(const PairView& pv, const CandBuf& cb, int li
 }
 
 // returns false when a larger score exists below
-__device__ inline bool stage_below(const PairView& pv, const CandBuf& cb, int li, int x, int y, uint32_t c, Scan& dn) {
+__device__ inline bool stage_below(const PairView& pv, const CandBuf& cb, int li, int x, int y, uint32_t c, Scan& dn, int center = -1) {
     dn = neutral_scan();
     if (li == 0) return true;
     const Geom& g = *pv.g;
-    const int center = pv.m.S[pv.off(li) + y * g.L[li].w + x];
+    if (center < 0) center = pv.m.S[pv.off(li) + y * g.L[li].w + x];
     const Footprint fb = scan_footprint(true, li, x, y);
     Window4 wb;
     wb.load(pv.m.S + pv.off(li - 1), g.L[li - 1].w, g.L[li - 1].h, window_origin(fb.x_1, fb.x1), window_origin(fb.y_1, fb.y1));
@@ -166,10 +167,11 @@ __device__ inline void stage_emit(const PairView& pv, const CandBuf& cb, const D
 }
 
 // the three stages back to back (phase B and the CPU harness; phase A re-packs candidates between the stages)
-__device__ inline void after_max2d(const PairView& pv, const CandBuf& cb, const DeviceTables& tb, int li, int x, int y, uint32_t c) {
+__device__ inline void after_max2d(const PairView& pv, const CandBuf& cb, const DeviceTables& tb, int li, int x, int y, uint32_t c,
+                                   int center = -1) {
     Scan up, dn;
-    if (!stage_above(pv, cb, li, x, y, c, up)) return;
-    if (!stage_below(pv, cb, li, x, y, c, dn)) return;
+    if (!stage_above(pv, cb, li, x, y, c, up, center)) return;
+    if (!stage_below(pv, cb, li, x, y, c, dn, center)) return;
     stage_emit(pv, cb, tb, li, x, y, c, up, dn);
 }
 
