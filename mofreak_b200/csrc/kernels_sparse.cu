@@ -172,6 +172,12 @@ __device__ __forceinline__ void group_sync(int grp) {
 // Shared memory of one block (dynamic: 27 bytes per list slot, PB_LIST slots shared by the block's pairs).  The candidates'
 // coordinates and, for the winners of a round, their own scores travel with the lists, so that a round costs four dependent
 // global-memory round trips (tie window; scan above; scan below; own patch) instead of seven.
+//
+// The groups of a block advance IN STEP: block-wide barriers align the phases of a round (verdicts | re-packing | scans of the
+// winners), and a group without work in a round waits.  The kernel is 6 K instructions (~100 KB) and every group follows its own
+// pair; left to themselves the warps of an SM sit at different places of that code and the kernel stalls on instruction fetch
+// (ncu, one warp per pair, free-running: 74 % of the stall samples "no instruction").  In step, the warps of a block execute
+// the same code region at the same time.
 template <int G>
 __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
     constexpr int PER = PB_THREADS / G;          // pairs per block
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
     __shared__ int warp_cnt[PB_THREADS / 32];
     const int grp = threadIdx.x / G, t = threadIdx.x % G;
     const int f = blockIdx.x * PER + grp;
-    if (f >= g.F) return;                        // whole groups leave; every barrier below is per group
+    const bool active = f < g.F;                 // groups beyond the last pair only keep the block's barriers company
     // per pair: list[2][LIST] | list_xy[2][LIST] | passed[LIST] | passed_xy[LIST] | verdict[LIST] | center[LIST] | passed_center[LIST]
     uint32_t* mine = pb_smem + (size_t)grp * (6 * LIST + 3 * LIST / 4);
     uint32_t (*list)[LIST] = reinterpret_cast<uint32_t (*)[LIST]>(mine);            // undecided tie candidates of this round / of the next
@@ -196,102 +202,96 @@ __global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ 
     volatile int& n_pass = ctl[grp][2];
     volatile int& more = ctl[grp][3];
     int* const wc = warp_cnt + grp * (G / 32);
-    PairView pv; pv.g = &g; pv.m = m; pv.f = f;
+    PairView pv; pv.g = &g; pv.m = m; pv.f = active ? f : 0;
     const uint32_t cap = (uint32_t)g.cand_cap;
     // which layers have tie candidates at all: one load for the six counts instead of a dependent round trip per layer
     uint32_t pending_of[N_LAYERS];
 #pragma unroll
-    for (int li = 0; li < N_LAYERS; li++) pending_of[li] = cb.pend_count[pv.f * N_LAYERS + li];
+    for (int li = 0; li < N_LAYERS; li++) pending_of[li] = active ? cb.pend_count[pv.f * N_LAYERS + li] : 0u;
     for (int li = 0; li < N_LAYERS; li++) {
         const uint32_t n_pending = pending_of[li];
-        if (n_pending == 0) continue;
+        if (!__syncthreads_or(n_pending != 0)) continue;                 // no pair of this block has ties on this layer
         const LayerGeom& L = g.L[li];
         const size_t r0 = (size_t)pv.f * g.rows + L.row0;
-        const uint32_t begin = min(cb.row_count[r0], cap), end = min(cb.row_count[r0 + L.h], cap);
-        uint32_t cursor = begin;
+        uint32_t cursor = 0, end = 0;
+        if (n_pending) { cursor = min(cb.row_count[r0], cap); end = min(cb.row_count[r0 + L.h], cap); }
         const bool listed = n_pending <= (uint32_t)min((int)PEND_CAP, LIST);      // phase A's list holds them all and they fit (order is irrelevant then)
-        // candidates are in raster order, so taking the pending ones chunk by chunk keeps every dependency
-        // (always raster-earlier) inside the current or an already finished chunk
-        int again;                                      // `more`, read by every thread BEFORE thread 0 may clear it again
-        do {
-            if (t == 0) { n_list = 0; more = 0; }
-            group_sync<G>(grp);
-            uint32_t next_cursor = end;
-            if (listed) {
-                const uint32_t* src = cb.pend_list + (size_t)(pv.f * N_LAYERS + li) * PEND_CAP;
-                for (uint32_t i = t; i < n_pending; i += G) { const uint32_t c = src[i]; list[0][i] = c; lxy[0][i] = cb.xy[c]; }
-                if (t == 0) n_list = (int)n_pending;
-            } else
-            // gather up to LIST pending candidates starting at cursor, preserving order
-            for (uint32_t base = cursor; base < end; base += G) {
-                const uint32_t c = base + t;
-                const bool pend = c < end && (cb.flags[c] & ST_PENDING);
-                // ordered append: warp ballots + per-warp offsets
-                const unsigned bal = __ballot_sync(0xffffffffu, pend);
-                if ((t & 31) == 0) wc[t >> 5] = __popc(bal);
+        bool chunks_left = n_pending != 0;       // this group still has a chunk of tie candidates to stage
+        int nl = 0, cur = 0;
+        for (;;) {
+            // ---- a group whose list is empty stages its next chunk: candidates are in raster order, so taking the pending
+            // ones chunk by chunk keeps every dependency (always raster-earlier) inside the current or a finished chunk ----
+            if (nl == 0 && chunks_left) {
+                if (t == 0) { n_list = 0; more = 0; }
                 group_sync<G>(grp);
-                int before = n_list;
-                for (int w = 0; w < (int)(t >> 5); w++) before += wc[w];
-                int total = 0;
-                for (int w = 0; w < G / 32; w++) total += wc[w];
-                const int slot = before + __popc(bal & ((1u << (t & 31)) - 1u));
-                const bool fits = n_list + total <= LIST;
-                if (pend && fits) { list[0][slot] = c; lxy[0][slot] = cb.xy[c]; }
+                uint32_t next_cursor = end;
+                if (listed) {
+                    const uint32_t* src = cb.pend_list + (size_t)(pv.f * N_LAYERS + li) * PEND_CAP;
+                    for (uint32_t i = t; i < n_pending; i += G) { const uint32_t c = src[i]; list[0][i] = c; lxy[0][i] = cb.xy[c]; }
+                    if (t == 0) n_list = (int)n_pending;
+                } else
+                // gather up to LIST pending candidates starting at cursor, preserving order
+                for (uint32_t base = cursor; base < end; base += G) {
+                    const uint32_t c = base + t;
+                    const bool pend = c < end && (cb.flags[c] & ST_PENDING);
+                    // ordered append: warp ballots + per-warp offsets
+                    const unsigned bal = __ballot_sync(0xffffffffu, pend);
+                    if ((t & 31) == 0) wc[t >> 5] = __popc(bal);
+                    group_sync<G>(grp);
+                    int before = n_list;
+                    for (int w = 0; w < (int)(t >> 5); w++) before += wc[w];
+                    int total = 0;
+                    for (int w = 0; w < G / 32; w++) total += wc[w];
+                    const int slot = before + __popc(bal & ((1u << (t & 31)) - 1u));
+                    const bool fits = n_list + total <= LIST;
+                    if (pend && fits) { list[0][slot] = c; lxy[0][slot] = cb.xy[c]; }
+                    group_sync<G>(grp);
+                    if (!fits) { next_cursor = base; if (t == 0) more = 1; break; }
+                    if (t == 0) n_list += total;
+                    group_sync<G>(grp);
+                }
                 group_sync<G>(grp);
-                if (!fits) { next_cursor = base; if (t == 0) more = 1; break; }
-                if (t == 0) n_list += total;
-                group_sync<G>(grp);
+                nl = n_list; cur = 0;
+                cursor = next_cursor;
+                chunks_left = more != 0;
+                group_sync<G>(grp);              // `more` and n_list were read by every thread before thread 0 may clear them again
+#ifdef MFK_PB_STATS
+                if (t == 0) atomicAdd(&cb.counters[5], (uint32_t)nl);
+#endif
             }
-            group_sync<G>(grp);
-            // fixed point over this chunk: every round decides all candidates whose raster-earlier tie neighbours are
-            // final (from the previous round's statuses), re-packs the winners and the still-waiting ones, then runs the
-            // scans of the winners one per thread
-            int nl = n_list, cur = 0;
+            if (!__syncthreads_or(nl > 0)) break;                        // every pair of the block is done with this layer
+            // ---- one round of the fixed point: every candidate whose raster-earlier tie neighbours are final (from the
+            // previous round's statuses) is decided; winners and still-waiting ones are re-packed; the winners' scans run ----
 #ifdef MFK_PB_STATS
-            int rounds = 0;
-            if (t == 0) atomicAdd(&cb.counters[5], (uint32_t)nl);
+            if (t == 0 && nl > 0) { atomicAdd(&cb.counters[4], 1u); atomicAdd(&cb.counters[7], (uint32_t)nl); }
 #endif
-            while (nl > 0) {
-#ifdef MFK_PB_STATS
-                rounds++;
-                if (t == 0) { atomicAdd(&cb.counters[4], 1u); atomicAdd(&cb.counters[7], (uint32_t)nl); }
-#endif
-                if (t == 0) { n_next = 0; n_pass = 0; }
-                for (int i = t; i < nl; i += G) {
-                    const uint32_t xy = lxy[cur][i];
-                    TieWindow tw;
-                    tw.load(pv, li, xy & 0xffff, xy >> 16);
-                    verdict[i] = earlier_pending_nearby(tw) ? 0 : (tie_break(tw) ? 2 : 1);
-                    center[i] = (uint8_t)packed_byte(tw.S[3], 3);
-                }
-                group_sync<G>(grp);
-                for (int i = t; i < nl; i += G) {
-                    const uint32_t c = list[cur][i], xy = lxy[cur][i];
-                    const uint8_t v = verdict[i];
-                    if (v == 0) { const int k = atomicAdd(&ctl[grp][1], 1); list[cur ^ 1][k] = c; lxy[cur ^ 1][k] = xy; }   // still waiting (order is irrelevant)
-                    else if (v == 2) { const int k = atomicAdd(&ctl[grp][2], 1); passed[k] = c; passed_xy[k] = xy; passed_center[k] = center[i]; }
-                    else { pv.m.status[pv.off(li) + (xy >> 16) * L.w + (xy & 0xffff)] = 0; cb.flags[c] = 0; }
-                }
-                group_sync<G>(grp);
-                const int np = n_pass;
-                for (int i = t; i < np; i += G) {
-                    const uint32_t xy = passed_xy[i];
-                    after_max2d(pv, cb, tb, li, xy & 0xffff, xy >> 16, passed[i], passed_center[i]);
-                }
-                __threadfence_block();
-                group_sync<G>(grp);
-                nl = n_next; cur ^= 1;
-                group_sync<G>(grp);
+            if (t == 0) { n_next = 0; n_pass = 0; }
+            for (int i = t; i < nl; i += G) {
+                const uint32_t xy = lxy[cur][i];
+                TieWindow tw;
+                tw.load(pv, li, xy & 0xffff, xy >> 16);
+                verdict[i] = earlier_pending_nearby(tw) ? 0 : (tie_break(tw) ? 2 : 1);
+                center[i] = (uint8_t)packed_byte(tw.S[3], 3);
             }
-#ifdef MFK_PB_STATS
-            if (t == 0) atomicMax(&cb.counters[6], (uint32_t)rounds);
-#endif
-            cursor = next_cursor;
-            again = more;
-            group_sync<G>(grp);
-        } while (again);
-        __threadfence_block();  // this group wrote the seen marks of layer li+1 that matter to it (phase A's are complete since its kernels ended)
-        group_sync<G>(grp);
+            __syncthreads();
+            for (int i = t; i < nl; i += G) {
+                const uint32_t c = list[cur][i], xy = lxy[cur][i];
+                const uint8_t v = verdict[i];
+                if (v == 0) { const int k = atomicAdd(&ctl[grp][1], 1); list[cur ^ 1][k] = c; lxy[cur ^ 1][k] = xy; }   // still waiting (order is irrelevant)
+                else if (v == 2) { const int k = atomicAdd(&ctl[grp][2], 1); passed[k] = c; passed_xy[k] = xy; passed_center[k] = center[i]; }
+                else { pv.m.status[pv.off(li) + (xy >> 16) * L.w + (xy & 0xffff)] = 0; cb.flags[c] = 0; }
+            }
+            __syncthreads();
+            const int np = nl > 0 ? n_pass : 0;
+            for (int i = t; i < np; i += G) {
+                const uint32_t xy = passed_xy[i];
+                after_max2d(pv, cb, tb, li, xy & 0xffff, xy >> 16, passed[i], passed_center[i]);
+            }
+            __threadfence_block();               // statuses and seen marks written by this group are read by it in the next round / layer
+            __syncthreads();
+            if (nl > 0) { nl = n_next; cur ^= 1; }
+            __syncthreads();                     // n_next was read before thread 0 clears it
+        }
     }
 }
 

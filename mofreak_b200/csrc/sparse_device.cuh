@@ -166,12 +166,28 @@ __device__ inline void stage_emit(const PairView& pv, const CandBuf& cb, const D
     cb.flags[c] = st;
 }
 
-// the three stages back to back (phase B and the CPU harness; phase A re-packs candidates between the stages)
+// the three stages back to back (phase B and the CPU harness; phase A re-packs candidates between the stages).  The two
+// scans run through ONE copy of the scan code with a run-time side (above first, then below, as refine3D does): phase B's
+// warps each follow their own pair, so the kernel is bound by instruction fetch, and two inlined copies of the scan are a
+// third of its code.
 __device__ inline void after_max2d(const PairView& pv, const CandBuf& cb, const DeviceTables& tb, int li, int x, int y, uint32_t c,
                                    int center = -1) {
-    Scan up, dn;
-    if (!stage_above(pv, cb, li, x, y, c, up, center)) return;
-    if (!stage_below(pv, cb, li, x, y, c, dn, center)) return;
+    const Geom& g = *pv.g;
+    if (center < 0) center = pv.m.S[pv.off(li) + y * g.L[li].w + x];
+    Scan up = neutral_scan(), dn = neutral_scan();
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+        const bool below = side != 0;
+        const int ln = below ? li - 1 : li + 1;                   // the neighbouring layer
+        if (ln < 0 || ln >= N_LAYERS) continue;
+        const Footprint fp = scan_footprint(below, li, x, y);
+        Window4 wn;
+        wn.load(pv.m.S + pv.off(ln), g.L[ln].w, g.L[ln].h, window_origin(fp.x_1, fp.x1), window_origin(fp.y_1, fp.y1));
+        const Scan sc = scan_neighbour(wn, fp, below, li, x, y, center);
+        if (!below) wn.flush_marks(pv.m.seen + pv.off(ln));       // getScoreMaxAbove's write-backs, even on early exit
+        if (!sc.ismax) { finish_failed(pv, cb, li, x, y, c); return; }
+        if (below) dn = sc; else up = sc;
+    }
     stage_emit(pv, cb, tb, li, x, y, c, up, dn);
 }
 
