@@ -8,6 +8,7 @@ sequence - the figures bench.py cannot measure live and reports in `roofline_iss
 import csv
 import json
 import os
+import re
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -47,7 +48,8 @@ def main():
     ik = hdr.index("Kernel Name")
     out, fam_inst, fam_dram, fam_us, seen_seq = [], {}, {}, {}, set()
     for r in data:
-        name = r[ik].split("(")[0].split("::")[-1].split("<")[0].strip()
+        km = re.search(r"(k_[a-z0-9_]+)", r[ik])
+        name = km.group(1) if km else r[ik].split("(")[0]
         rec = {"kernel": name}
         for k, _ in COLS:
             i = idx[k]
