@@ -410,8 +410,11 @@ def run_ours(args, name, cfg):
         i_in = np.arange(P)
 
         def submit(e):
+            """All uploads of the turn first (the copy stream never waits for the host to finish queuing kernels), then the
+            extractions: every launch sequence waits only for the uploads that carry its own frames (per-upload events)."""
             c = e["ctx"]
             c.reset_rows()
+            todo = []
             for _ in range(SEGS):
                 k = e["seg"]
                 q = k % (2 * SEGS)                                         # ring segment this pass writes
@@ -426,9 +429,11 @@ def run_ours(args, name, cfg):
                         cu.append(base + q * P + i_in)
                         pr.append(base + (q * P + i_in - GAP) % ring)      # 5 frames earlier in the ring
                         lb.append(k * P + i_in + GAP - 1)
-                    c.extract_pairs(np.concatenate(cu), np.concatenate(pr), np.concatenate(lb))
+                    todo.append((np.concatenate(cu), np.concatenate(pr), np.concatenate(lb)))
                     j0 += n_s
                 e["seg"] = k + 1
+            for cu, pr, lb in todo:
+                c.extract_pairs(cu, pr, lb)
         h2d_per_step = V * P * frame_bytes
     else:
         # clips: whole steps alternate between two contexts; a step uploads every frame of every clip
@@ -442,10 +447,16 @@ def run_ours(args, name, cfg):
         def submit(e):
             c = e["ctx"]
             c.reset_rows()
-            for v0 in range(0, V, chunk_v):
+            # the clips of a chunk are adjacent in the host buffer (HPV == FPV in clips mode): one copy per chunk, queued two
+            # chunks ahead of the extraction that needs it (each launch sequence waits only for its own chunk's upload)
+            starts = list(range(0, V, chunk_v))
+            nxt = 0
+            for i, v0 in enumerate(starts):
+                while nxt < min(len(starts), i + 3):
+                    u0 = starts[nxt]; u1 = min(V, u0 + chunk_v)
+                    c.upload_raw(host.ptr + u0 * FPV * frame_bytes, (u1 - u0) * FPV, u0 * FPV)
+                    nxt += 1
                 v1 = min(V, v0 + chunk_v)
-                # the clips of a chunk are adjacent in the host buffer (HPV == FPV in clips mode): one copy
-                c.upload_raw(host.ptr + v0 * FPV * frame_bytes, (v1 - v0) * FPV, v0 * FPV)
                 ps = slice(v0 * P, v1 * P)
                 c.extract_pairs(cur[ps], prev[ps], label[ps])
         h2d_per_step = n_frames * frame_bytes

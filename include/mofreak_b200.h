@@ -60,8 +60,8 @@ typedef struct mfk_row {
  * Replaces: new MoFREAKUtilities(dataset) + the per-frame new BriskFeatureDetector(30) / cv::FREAK
  * construction of MoFREAKUtilities.cpp:420-427 (all tables are built once here).
  * Device memory: the store plus four sets ("lanes") of per-launch-sequence buffers, about 11 MB per pair and set at
- * 720x576 (27 B per frame pixel), i.e. ~11 GB for max_pairs = 256; the environment variable MFK_LANES = 1..4 lowers
- * the number of sets (less memory, less overlap between consecutive launch sequences). */
+ * 720x576 (27 B per frame pixel), i.e. ~11 GB for max_pairs = 256; the environment variable MFK_LANES = 1..8 sets
+ * the number of sets (default 4; fewer = less memory and less overlap between consecutive launch sequences; more measured no gain). */
 int  mfk_create(mfk_ctx** out, int device, int width, int height, int store_frames, int max_pairs);
 /* Same, with explicit per-pair budgets (0 = default) for detector candidates and output rows. */
 int  mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_frames, int max_pairs,

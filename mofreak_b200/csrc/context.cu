@@ -60,6 +60,17 @@ struct mfk_ctx {
     };
     ReadRec readers[8];                   // which slot ranges recent launch sequences still read
     int reader_next = 0;
+    // the mirror image: which slots recent uploads fill, each with its own event on the copy stream, so that a launch sequence
+    // waits only for the uploads that carry ITS frames (a caller may queue all uploads of a step first and the extractions
+    // after them without serialising the first extraction behind the last upload).  Records leave the ring in upload order;
+    // `writers_folded` is the event of the newest record that left: the copy stream is in order, so waiting for it covers
+    // every upload that is no longer tracked.
+    struct WriteRec { int lo = 0, hi = -1; cudaEvent_t ev = nullptr; bool valid = false; };
+    enum { N_WRITERS = 256 };
+    WriteRec writers[N_WRITERS];
+    int writer_next = 0;
+    cudaEvent_t writers_folded = nullptr;
+    bool writers_folded_valid = false;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     // geometry template (F filled per batch)
     int lw[N_LAYERS], lh[N_LAYERS], rows = 0, pyr_px = 0;
@@ -215,6 +226,16 @@ int upload_tables(mfk_ctx* c) {
     return MFK_OK;
 }
 
+// the copy stream has just been given the upload of slots [lo, hi]: remember it with an event of its own
+int note_upload(mfk_ctx* c, int lo, int hi) {
+    mfk_ctx::WriteRec& w = c->writers[c->writer_next];
+    c->writer_next = (c->writer_next + 1) % mfk_ctx::N_WRITERS;
+    if (w.valid) { std::swap(w.ev, c->writers_folded); c->writers_folded_valid = true; }      // the oldest record leaves the ring
+    CU(c, cudaEventRecord(w.ev, c->copy_stream));
+    w.lo = lo; w.hi = hi; w.valid = true;
+    return MFK_OK;
+}
+
 // orders everything queued on the lanes before whatever is queued on the main stream next
 int join_lanes(mfk_ctx* c) {
     for (int i = 0; i < c->lanes_built; i++) {
@@ -350,6 +371,8 @@ void destroy(mfk_ctx* c) {
     if (c->upload_done) cudaEventDestroy(c->upload_done);
     if (c->main_mark) cudaEventDestroy(c->main_mark);
     for (auto& r : c->readers) for (cudaEvent_t e : r.ev) if (e) cudaEventDestroy(e);
+    for (auto& wr : c->writers) if (wr.ev) cudaEventDestroy(wr.ev);
+    if (c->writers_folded) cudaEventDestroy(c->writers_folded);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -461,6 +484,8 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
         CUC(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
     }
     for (auto& r : c->readers) for (auto& e : r.ev) CUC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& wr : c->writers) CUC(cudaEventCreateWithFlags(&wr.ev, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&c->writers_folded, cudaEventDisableTiming));
     CUC(cudaEventCreate(&c->t0));
     CUC(cudaEventCreate(&c->t1));
     // pyramid geometry, brisk.cpp:1660, 1666
@@ -565,6 +590,7 @@ int mfk_upload_frames(mfk_ctx* c, const uint8_t* gray, size_t stride, int n_fram
         else
             CU(c, cudaMemcpy2DAsync(c->store + (size_t)slot * px, c->W, src, stride, c->W, (size_t)run * c->H,
                                     cudaMemcpyHostToDevice, c->copy_stream));
+        { const int rc = note_upload(c, slot, slot + run - 1); if (rc != MFK_OK) return rc; }
         done += run;
     }
     CU(c, cudaEventRecord(c->upload_done, c->copy_stream));
@@ -600,6 +626,7 @@ int mfk_upload_frames_bgr(mfk_ctx* c, const uint8_t* bgr, size_t stride, int n_f
         uint8_t* dst = c->store + (size_t)slot * px;
         launch_bgr2gray(c->copy_stream, c->bgr_stage, dst, (size_t)run * px, coeff_bits);
         c->launches++;
+        { const int rc = note_upload(c, slot, slot + run - 1); if (rc != MFK_OK) return rc; }
         done += run;
     }
     CU(c, cudaEventRecord(c->upload_done, c->copy_stream));
@@ -625,25 +652,8 @@ int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_s
     if (rc != MFK_OK) return rc;
     const size_t first = c->pairs_queued;
     c->upload_pending = false;
-    // The lane-private front of a launch sequence (difference image, pyramid, scores, NMS) only waits for the frames;
-    // its shared-row part is additionally ordered after whatever the caller queued on the main stream before this
-    // call (run_batch, main_wait_pending).  So the front of this call overlaps the tail of the previous one.
-    CU(c, cudaEventRecord(c->main_mark, c->stream));
-    c->main_wait_pending = true;
-    bool touched[mfk_ctx::MAX_LANES] = {};
-    for (int done = 0; done < n_pairs; done += c->max_pairs) {
-        const int F = std::min(c->max_pairs, n_pairs - done);
-        const int li = (int)(c->batches % (uint64_t)c->n_lanes);
-        if (!touched[li]) {
-            CU(c, cudaStreamWaitEvent(c->lane[li].stream, c->upload_done, 0));
-            touched[li] = true;
-        }
-        rc = run_batch(c, cur_slot + done, prev_slot + done, label + done, first + done, F);
-        if (rc != MFK_OK) return rc;
-    }
-    c->pairs_queued += (size_t)n_pairs;
-    // remember which slots this call reads until its kernels have run: the distinct slots as maximal runs of consecutive
-    // slots; more runs than a record holds collapse into one conservative [min, max] range
+    // the slots this call reads, as maximal runs of consecutive slots; more runs than a record holds collapse into one
+    // conservative [min, max] range
     std::vector<int> slots;
     slots.reserve(2 * (size_t)n_pairs);
     for (int i = 0; i < n_pairs; i++) { slots.push_back(cur_slot[i] % c->store_frames); slots.push_back(prev_slot[i] % c->store_frames); }
@@ -659,6 +669,29 @@ int mfk_extract_pairs(mfk_ctx* c, const int32_t* cur_slot, const int32_t* prev_s
         i = j + 1;
     }
     if (too_many) { iv_lo[0] = slots.front(); iv_hi[0] = slots.back(); n_iv = 1; }
+    // The lane-private front of a launch sequence (difference image, pyramid, scores, NMS) only waits for the uploads that
+    // carry its frames; its shared-row part is additionally ordered after whatever the caller queued on the main stream
+    // before this call (run_batch, main_wait_pending).  So the front of this call overlaps the tail of the previous one.
+    CU(c, cudaEventRecord(c->main_mark, c->stream));
+    c->main_wait_pending = true;
+    bool touched[mfk_ctx::MAX_LANES] = {};
+    for (int done = 0; done < n_pairs; done += c->max_pairs) {
+        const int F = std::min(c->max_pairs, n_pairs - done);
+        const int li = (int)(c->batches % (uint64_t)c->n_lanes);
+        if (!touched[li]) {
+            if (c->writers_folded_valid) CU(c, cudaStreamWaitEvent(c->lane[li].stream, c->writers_folded, 0));
+            for (const mfk_ctx::WriteRec& w : c->writers) {
+                if (!w.valid) continue;
+                bool hit = false;
+                for (int k = 0; k < n_iv && !hit; k++) hit = w.lo <= iv_hi[k] && w.hi >= iv_lo[k];
+                if (hit) CU(c, cudaStreamWaitEvent(c->lane[li].stream, w.ev, 0));
+            }
+            touched[li] = true;
+        }
+        rc = run_batch(c, cur_slot + done, prev_slot + done, label + done, first + done, F);
+        if (rc != MFK_OK) return rc;
+    }
+    c->pairs_queued += (size_t)n_pairs;
     mfk_ctx::ReadRec& rec = c->readers[c->reader_next];
     c->reader_next = (c->reader_next + 1) % 8;
     if (rec.valid)          // recycled record: keep its ordering

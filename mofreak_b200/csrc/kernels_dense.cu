@@ -261,8 +261,7 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     // ---- stage: item (r, j) = 8 pixels x0-4+8j .. of image row y0-3+r (clamped); pixels outside the row read as 0 - they
     // are only ever ring pixels of border centres, which are not scored ----
     const bool word_rows = ((((uintptr_t)img) | (uintptr_t)w) & 3) == 0;      // every staged item then starts on a word of the image
-    for (int i = tid; i < SC_SH * (SC_SW / 8); i += 256) {
-        const int r = i / (SC_SW / 8), j = i - r * (SC_SW / 8);
+    auto stage_item = [&](const int r, const int j) {
         const int gy = min(max(y0 - 3 + r, 0), h - 1);
         const int gx = x0 - 4 + 8 * j;
         const uint8_t* p = img + gy * w + gx;
@@ -270,8 +269,10 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
         if (word_rows && gx >= 0 && gx + 12 <= w) {                         // interior of the row: three aligned words
             const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
             w0 = q[0]; w1 = q[1]; w2 = q[2];
+        } else if (gx >= w) {                                                // right of the image: nothing to read
+            w0 = w1 = w2 = 0u;
         } else {
-            w0 = (gx >= 0 && gx < w) ? load4(p) : 0u;
+            w0 = (gx >= 0) ? load4(p) : 0u;
             w1 = (gx + 4 < w) ? load4(p + 4) : 0u;                          // gx + 4 >= 0 always
             w2 = (gx + 8 < w) ? load4(p + 8) : 0u;
         }
@@ -279,7 +280,12 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
         widen8(w0, w1, w2, ev, od);
         *reinterpret_cast<uint4*>(&E[r][4 * j]) = ev;
         *reinterpret_cast<uint4*>(&O[r][4 * j]) = od;
-    }
+    };
+    // 38 rows x 9 items, at most two per thread and no index division: the first 32 rows x 8 items are one item per thread,
+    // the remaining 6 rows x 8 items and the ninth item of all 38 rows go to the first 86 threads
+    stage_item(tid >> 3, tid & 7);
+    if (tid < (SC_SH - 32) * 8) stage_item(32 + (tid >> 3), tid & 7);
+    else if (tid < (SC_SH - 32) * 8 + SC_SH) stage_item(tid - (SC_SH - 32) * 8, 8);
     if (tid < SC_TH) row_hits[tid] = 0ull;
     reinterpret_cast<unsigned long long*>(&score_tile[0][0])[tid] = 0ull;          // 256 threads x 8 bytes = the tile
     __syncthreads();

@@ -160,6 +160,9 @@ void launch_phase_a(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTa
 // threads.  So the group size follows the frame size - one WARP per pair for small frames (__syncwarp, eight pairs per
 // block), named barriers for 64 / 128 threads, the whole block (__syncthreads) for large frames.
 constexpr int PB_THREADS = 256;
+#ifndef PB_BLOCKS_PER_SM
+#define PB_BLOCKS_PER_SM 3
+#endif
 constexpr int PB_LIST = PEND_CAP;  // tie candidates of one (pair, layer) staged in shared memory per sweep, for G = 256
 
 template <int G>
@@ -179,7 +182,7 @@ __device__ __forceinline__ void group_sync(int grp) {
 // (ncu, one warp per pair, free-running: 74 % of the stall samples "no instruction").  In step, the warps of a block execute
 // the same code region at the same time.
 template <int G>
-__global__ void __launch_bounds__(PB_THREADS) k_phase_b(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
+__global__ void __launch_bounds__(PB_THREADS, PB_BLOCKS_PER_SM) k_phase_b(const __grid_constant__ Geom g, Maps m, CandBuf cb, DeviceTables tb) {
     constexpr int PER = PB_THREADS / G;          // pairs per block
     constexpr int LIST = PB_LIST / PER;          // list capacity of one pair
     extern __shared__ __align__(16) uint32_t pb_smem[];

@@ -177,6 +177,24 @@ def test_ring_wraparound_and_arbitrary_pair_order(orc):
     assert util.rows_equal(rows, np.concatenate(parts))
 
 
+def test_uploads_queued_ahead_of_their_extractions(orc):
+    """A launch sequence waits only for the uploads that carry its frames (per-upload events); records that fall out of the
+    event ring (more than 256 uploads in flight) fold into an in-order event.  All frames are uploaded one by one FIRST - more
+    uploads than the ring holds, the ring wrapping twice over its slots - then every pair is extracted."""
+    clip = mofreak_b200.synth_clip(160, 120, 40, 91)
+    want = orc.extract_clip(clip)
+    with mofreak_b200.Context(160, 120, 40, 8) as ctx:
+        for rep in range(8):                                         # 320 single-frame uploads, the last pass holds the clip
+            src = clip if rep == 7 else np.roll(clip, rep + 1, axis=0)
+            for k in range(40):
+                ctx.upload_frames(src[k:k + 1], k)
+        cur = np.arange(5, 40, dtype=np.int32)
+        for a in range(0, len(cur), 5):                              # several extraction calls after all the uploads
+            ctx.extract_pairs(cur[a:a + 5], cur[a:a + 5] - 5, cur[a:a + 5] - 1)
+        rows, _ = ctx.fetch_rows(200000)
+    assert util.rows_equal(rows, want), util.describe_diff(rows, want)
+
+
 def test_capacity_overflow_is_reported_not_silent():
     clip = mofreak_b200.synth_clip(320, 240, 7, 71)
     with mofreak_b200.Context(320, 240, 16, 2, cand_cap_per_pair=64, row_cap_per_pair=8) as ctx:
