@@ -86,10 +86,13 @@ struct mfk_ctx {
         int32_t* integral_left = nullptr;
         unsigned long long* hitmask = nullptr;  // detector hits, one 64-bit word per (pair, layer row, 64-column tile)     // per image row: sums left of each 32-column strip
         CandBuf cb{};
+        ScoreMapCache score_maps;
         int32_t* pairs = nullptr;                // this batch's pair descriptions: cur | prev | label, max_pairs each
         uint32_t* scan_scratch = nullptr;
-        cudaStream_t stream = nullptr, aux_stream = nullptr;
-        cudaEvent_t aux_fork = nullptr, aux_join = nullptr, advanced = nullptr, done = nullptr;
+        // stream: the lane's spine (small kernels, descriptor kernel; high priority).  dense_stream: k_front + k_scores, the two
+        // kernels whose grids fill every SM for their whole duration (low priority); aux_stream: the integral image (low).
+        cudaStream_t stream = nullptr, dense_stream = nullptr, aux_stream = nullptr;
+        cudaEvent_t aux_fork = nullptr, aux_join = nullptr, advanced = nullptr, done = nullptr, prepared = nullptr, scored = nullptr;
         bool used = false;
         int seen_F = -1;                         // batch size the `seen` map was last cleared for (layer bases depend on it)
     };
@@ -98,6 +101,8 @@ struct mfk_ctx {
     bool reset_pending = false;           // mfk_reset_rows is applied in-line by the next launch sequence (or by settle())
     bool main_wait_pending = false;       // the next launch sequence orders its shared-row part after main_mark
     bool serial = false;
+    bool prioritised = true;              // MFK_PRIORITY=0: one stream per lane (plus the integral side stream), no priorities
+    bool early_compact = true;            // MFK_EARLY_COMPACT=0: the whole second compaction waits for the previous tail
     bool fused_front = true;              // MFK_FUSED_FRONT=0 forces the separate dense kernels (A/B measurements, wide frames use them anyway)
     uint64_t batches = 0;
     int last_lane = 0;
@@ -262,6 +267,7 @@ int sync_all(mfk_ctx* c) {
     CU(c, cudaStreamSynchronize(c->copy_stream));
     for (int i = 0; i < c->lanes_built; i++) {
         if (c->lane[i].aux_stream) CU(c, cudaStreamSynchronize(c->lane[i].aux_stream));
+        if (c->lane[i].dense_stream) CU(c, cudaStreamSynchronize(c->lane[i].dense_stream));
         if (c->lane[i].stream) CU(c, cudaStreamSynchronize(c->lane[i].stream));
     }
     CU(c, cudaStreamSynchronize(c->stream));
@@ -297,41 +303,52 @@ int run_batch(mfk_ctx* c, const int32_t* cur, const int32_t* prev, const int32_t
     else { CU(c, cudaMemsetAsync(L.maps.seen, 0, (size_t)c->max_pairs * c->pyr_px, st)); L.seen_F = F; }
     CU(c, cudaMemsetAsync(L.cb.pend_count, 0, (size_t)F * N_LAYERS * sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(L.cb.q_count, 0, 4 * sizeof(uint32_t), st));
-    // dense front: one fused kernel (difference, pyramid, row sums) for frames up to 2048 wide, the separate kernels beyond
+    // dense front: one fused kernel (difference, pyramid, row sums) for frames up to 2048 wide, the separate kernels beyond.
+    // It and the score kernel run on the lane's LOW-priority stream: their grids fill every SM for their whole duration, and
+    // at equal priority the block scheduler hands the small dependent kernels of the other launch sequences (scans,
+    // compactions, NMS phases: each a few blocks that wait on the previous one) their SM slots only when such a grid has been
+    // dispatched completely - measured with mfk_profile_timeline: 1.1 ms for the five tiny kernels of the second compaction,
+    // which run in 0.08 ms on an idle GPU, on the path that serialises the launch sequences.
     const bool fused = c->fused_front && front_supported(g);
-    if (fused) { Span s(c, P_FRONT, 1, st); CU(c, launch_front(st, g, c->store, c->store_frames, pl, L.maps.img, L.integral_left)); }
-    else { Span s(c, P_ABSDIFF, 1, st);   launch_absdiff(st, g, c->store, c->store_frames, pl, L.maps.img); }
+    cudaStream_t ds = (c->serial || !L.dense_stream) ? st : L.dense_stream;
+    if (ds != st) { CU(c, cudaEventRecord(L.prepared, st)); CU(c, cudaStreamWaitEvent(ds, L.prepared, 0)); }
+    if (fused) { Span s(c, P_FRONT, 1, ds); CU(c, launch_front(ds, g, c->store, c->store_frames, pl, L.maps.img, L.integral_left)); }
+    else { Span s(c, P_ABSDIFF, 1, ds);   launch_absdiff(ds, g, c->store, c->store_frames, pl, L.maps.img); }
     // the integral image only needs layer 0: fork it onto the side stream, join before the descriptor kernel
     if (c->serial) {
         Span s(c, P_INTEGRAL, fused ? 1 : 2, st);  launch_integral(st, g, L.maps.img, L.integral, L.integral_left, fused);
     } else {
-        CU(c, cudaEventRecord(L.aux_fork, st));
+        CU(c, cudaEventRecord(L.aux_fork, ds));
         CU(c, cudaStreamWaitEvent(L.aux_stream, L.aux_fork, 0));
         { Span s(c, P_INTEGRAL, fused ? 1 : 2, L.aux_stream);  launch_integral(L.aux_stream, g, L.maps.img, L.integral, L.integral_left, fused); }
         CU(c, cudaEventRecord(L.aux_join, L.aux_stream));
     }
-    if (!fused) { Span s(c, P_PYRAMID, 5, st);   launch_pyramid(st, g, L.maps.img); }
-    { Span s(c, P_SCORES, 1, st);    launch_scores(st, g, L.maps.img, L.maps.S, L.hitmask); }
+    if (!fused) { Span s(c, P_PYRAMID, 5, ds);   launch_pyramid(ds, g, L.maps.img); }
+    { Span s(c, P_SCORES, 1, ds);    launch_scores(ds, g, L.maps.img, L.maps.S, L.hitmask, L.score_maps); }
+    if (ds != st) { CU(c, cudaEventRecord(L.scored, ds)); CU(c, cudaStreamWaitEvent(st, L.scored, 0)); }
     { Span s(c, P_SCAN, 4, st);      launch_row_counts(st, g, L.hitmask, L.cb.row_count);
                                      launch_exclusive_scan(st, L.cb.row_count, F * g.rows, nullptr, L.scan_scratch); }
     { Span s(c, P_FILL, 1, st);      launch_fill_candidates(st, g, L.hitmask, L.cb); }
     { Span s(c, P_PHASE_A, 4, st);   launch_phase_a(st, g, L.maps, L.cb, c->tb); }
     { Span s(c, P_PHASE_B, 1, st);   launch_phase_b(st, g, L.maps, L.cb, c->tb); }
-    // From here on batches run one after the other.  Only k_advance (this batch's base in the shared row accumulation, the
-    // counters) needs that; the second compaction and the descriptor kernel are lane-private, but letting them of several
+    // second ordered compaction, lane-private part: keep flags of the batch's candidates and their exclusive scan
+    auto keep_scan = [&]() {
+        Span s(c, P_COMPACT, 4, st);
+        launch_keep_flags(st, g, L.cb);
+        launch_exclusive_scan(st, L.cb.keep_scan, c->cand_cap, L.cb.live, L.scan_scratch);
+    };
+    if (c->early_compact) keep_scan();
+    // From here on batches run one after the other.  Only the advance step of k_scatter_rows (this batch's base in the shared row accumulation, the
+    // counters) and the per-pair row counts need that; the descriptor kernel is lane-private, but letting those of several
     // batches overlap measured 1-2 % slower (they gather from per-batch candidate arrays and integral images, and together
-    // thrash L2), so the whole tail waits for the previous batch's.  Also ordered here: whatever the caller queued on the
+    // thrash L2), so the tail waits for the previous batch's.  Also ordered here: whatever the caller queued on the
     // main stream before this call (bag-of-words reads of the rows, timers), and a pending row reset.
     if (c->batches > 0 && c->last_lane != li) CU(c, cudaStreamWaitEvent(st, P.advanced, 0));
     if (c->main_wait_pending) { CU(c, cudaStreamWaitEvent(st, c->main_mark, 0)); c->main_wait_pending = false; }
     if (c->reset_pending) { CU(c, cudaMemsetAsync(c->counters, 0, 4 * sizeof(uint32_t), st)); c->reset_pending = false; }
-    // second ordered compaction: kept keypoints -> row slots of this batch, per-pair row counts
-    { Span s(c, P_COMPACT, 5, st);
-      launch_keep_flags(st, g, L.cb);
-      launch_exclusive_scan(st, L.cb.keep_scan, c->cand_cap, L.cb.live, L.scan_scratch);
-      launch_scatter_rows(st, g, L.cb, c->pair_rows + first);
-    }
-    { Span s(c, P_COMPACT, 1, st);   launch_advance(st, g, L.cb); }
+    if (!c->early_compact) keep_scan();
+    // kept keypoints -> row slots of this batch, per-pair row counts, and this batch's base in the shared accumulation
+    { Span s(c, P_COMPACT, 1, st);   launch_scatter_rows(st, g, L.cb, c->pair_rows + first); }
     if (!c->serial) CU(c, cudaStreamWaitEvent(st, L.aux_join, 0));
     { Span s(c, P_DESCRIBE, 1, st);
       launch_describe(st, g, c->store, c->store_frames, pl, L.maps.img, L.integral, L.cb, c->tb, c->rows_buf);
@@ -357,8 +374,9 @@ void destroy(mfk_ctx* c) {
         cudaFree(L.cb.kresp); cudaFree(L.cb.flags); cudaFree(L.cb.scale_idx); cudaFree(L.cb.keep_scan); cudaFree(L.cb.row_src);
         cudaFree(L.cb.pend_count); cudaFree(L.cb.pend_list); cudaFree(L.cb.live);
         cudaFree(L.cb.q_count); cudaFree(L.cb.q0); cudaFree(L.cb.q1); cudaFree(L.cb.q2); cudaFree(L.cb.q1_up); cudaFree(L.cb.q2_scan); cudaFree(L.scan_scratch); cudaFree(L.pairs);
-        for (cudaEvent_t e : {L.aux_fork, L.aux_join, L.advanced, L.done}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {L.aux_fork, L.aux_join, L.advanced, L.done, L.prepared, L.scored}) if (e) cudaEventDestroy(e);
         if (L.aux_stream) cudaStreamDestroy(L.aux_stream);
+        if (L.dense_stream) cudaStreamDestroy(L.dense_stream);
         if (L.stream) cudaStreamDestroy(L.stream);
     }
     cudaFree(c->counters);
@@ -474,10 +492,22 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     if (const char* e = getenv("MFK_LANES")) c->lanes_built = std::max(1, std::min((int)mfk_ctx::MAX_LANES, atoi(e)));
     c->n_lanes = c->lanes_built;
     if (const char* e = getenv("MFK_FUSED_FRONT")) c->fused_front = atoi(e) != 0;
+    if (const char* e = getenv("MFK_PRIORITY")) c->prioritised = atoi(e) != 0;
+    if (const char* e = getenv("MFK_EARLY_COMPACT")) c->early_compact = atoi(e) != 0;
+    int prio_low = 0, prio_high = 0;
+    CUC(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
     for (int li = 0; li < c->lanes_built; li++) {
         mfk_ctx::Lane& L = c->lane[li];
-        CUC(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-        CUC(cudaStreamCreateWithFlags(&L.aux_stream, cudaStreamNonBlocking));
+        if (c->prioritised) {
+            CUC(cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, prio_high));
+            CUC(cudaStreamCreateWithPriority(&L.dense_stream, cudaStreamNonBlocking, prio_low));
+            CUC(cudaStreamCreateWithPriority(&L.aux_stream, cudaStreamNonBlocking, prio_low));
+        } else {
+            CUC(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+            CUC(cudaStreamCreateWithFlags(&L.aux_stream, cudaStreamNonBlocking));
+        }
+        CUC(cudaEventCreateWithFlags(&L.prepared, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&L.scored, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&L.aux_fork, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&L.aux_join, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&L.advanced, cudaEventDisableTiming));

@@ -88,10 +88,10 @@ __device__ __forceinline__ int round_half_up_nonneg(float t, int bias) {
     return i + bias + ((t - (float)i) >= 0.5f ? 1 : 0);
 }
 
-__device__ __forceinline__ int mean_intensity(const int32_t* __restrict__ I, int W1, const FreakPoint P, float kx, float ky) {
-    const float xf = P.x + kx;
-    const float yf = P.y + ky;
-    const float radius = P.sigma;
+__device__ __forceinline__ int mean_intensity(const int32_t* __restrict__ I, int W1, const float px, const float py, const float radius,
+                                              float kx, float ky) {
+    const float xf = px + kx;
+    const float yf = py + ky;
     const int x_left = round_half_up_nonneg(xf - radius, 0);
     const int y_top = round_half_up_nonneg(yf - radius, 0);
     const int x_right = round_half_up_nonneg(xf + radius, 1);
@@ -106,6 +106,10 @@ __device__ __forceinline__ int mean_intensity(const int32_t* __restrict__ I, int
     const int r = v - q * area;
     q += (r >= area) - (r < 0);
     return q & 0xff;
+}
+
+__device__ __forceinline__ int mean_intensity(const int32_t* __restrict__ I, int W1, const FreakPoint& P, float kx, float ky) {
+    return mean_intensity(I, W1, P.x, P.y, P.sigma, kx, ky);
 }
 
 // ---- cv::resize(ROI s x s -> 19 x 19, INTER_LINEAR, 8-bit) as OpenCV's fixed-point bilinear path computes it ----

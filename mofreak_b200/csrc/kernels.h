@@ -40,8 +40,8 @@ struct CandBuf {                  // ordered candidate list of the batch + per-c
     uint32_t q_cap;
     uint32_t* counters;           // shared by all batches: [0] overflow flags (1 candidates, 2 rows), [1] rows accumulated
                                   // so far, [2] pairs accumulated so far, [3] live candidates of the last batch (copy)
-    uint32_t* live;               // [0] live candidate count of THIS batch (per buffer set), [1] its overflow flags until k_advance,
-                                  // [2] row ticket counter of k_describe, [3] rows_base of this batch (both set by k_advance)
+    uint32_t* live;               // [0] live candidate count of THIS batch (per buffer set), [1] its overflow flags until the advance step,
+                                  // [2] row ticket counter of k_describe, [3] rows_base of this batch (both set by the advance step of k_scatter_rows)
 };
 
 enum { PEND_CAP = 2048 };         // per (pair, layer); beyond it phase B falls back to an ordered sweep
@@ -66,7 +66,13 @@ void launch_pyramid(cudaStream_t, const Geom&, uint8_t* img);                   
 int  score_mask_words(int frame_width);        // 64-bit hit-mask words per (pair, layer row)
 int  score_tile_rows(const int layer_heights[N_LAYERS]);   // tile rows of k_scores over all layers, and the table's capacity
 int  score_tile_rows_max();
-void launch_scores(cudaStream_t, const Geom&, const uint8_t* img, uint8_t* S, unsigned long long* hitmask);
+// k_scores' tensor maps of one lane's pyramid buffer (opaque here: CUtensorMap needs cuda.h), rebuilt when F or img change
+struct ScoreMapCache {
+    int F = -1;
+    const uint8_t* img = nullptr;
+    alignas(64) unsigned char blob[N_LAYERS * 128 + 64];
+};
+void launch_scores(cudaStream_t, const Geom&, const uint8_t* img, uint8_t* S, unsigned long long* hitmask, ScoreMapCache& cache);
 void launch_row_counts(cudaStream_t, const Geom&, const unsigned long long* hitmask, uint32_t* row_count);
 void launch_fill_candidates(cudaStream_t, const Geom&, const unsigned long long* hitmask, CandBuf);
 // left_done: the per-row strip sums were already written by launch_front
@@ -86,7 +92,6 @@ void launch_phase_a(cudaStream_t, const Geom&, Maps, CandBuf, DeviceTables);
 void launch_phase_b(cudaStream_t, const Geom&, Maps, CandBuf, DeviceTables);
 void launch_keep_flags(cudaStream_t, const Geom&, CandBuf);           // flags -> keep_scan input
 void launch_scatter_rows(cudaStream_t, const Geom&, CandBuf, uint32_t* pair_rows);   // after the scan: row_src, per-pair counts (pair_rows = this batch's slice)
-void launch_advance(cudaStream_t, const Geom&, CandBuf);              // counters += this batch
 void launch_describe(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, const uint8_t* img,
                      const int32_t* integral, CandBuf, DeviceTables, void* rows /*mfk_row*/);
 void launch_mip_only(cudaStream_t, int W, int H, const uint8_t* cur, const uint8_t* prev, const float* kp_xys, int n,

@@ -11,7 +11,10 @@
 // contraction, so tensor cores are not involved.
 #include "brisk_device.cuh"
 #include "dense_device.cuh"
+#include <cuda.h>
+
 #include "kernels.h"
+#include "tma_device.cuh"
 
 namespace mfk {
 
@@ -239,14 +242,29 @@ __device__ __forceinline__ void widen8(uint32_t w0, uint32_t w1, uint32_t w2, ui
     odd.z = __byte_perm(f1, 0, 0x4140); odd.w = __byte_perm(f1, 0, 0x4342);
 }
 
-__global__ void __launch_bounds__(256, 8)          // 8 blocks per SM: 32 registers, 18 KB of shared memory each
-k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tiles, const uint8_t* __restrict__ img_all,
-         uint8_t* __restrict__ S_all, unsigned long long* __restrict__ hitmask, int mask_words) {
+constexpr int SC_RAW = 96;                            // bytes per raw staged row of the tensor copy: columns x0-16 .. x0+79
+constexpr int SC_BOX_X = 12;                          // tensor copy: the box starts at column x0-16 (box starts must be 16-byte aligned in memory:
+                                                      // measured, an unaligned inner coordinate faults as an illegal instruction), i.e. 12 bytes before staged column 0
+
+struct ScoreMaps {                          // one 2-D tensor map per layer whose rows are 16-byte aligned (see launch_scores)
+    CUtensorMap map[N_LAYERS];
+    int use[N_LAYERS];
+};
+static_assert(sizeof(ScoreMaps) == sizeof(ScoreMapCache::blob), "ScoreMapCache::blob holds a ScoreMaps");
+
+__global__ void __launch_bounds__(256, 8)          // 8 blocks per SM: 32 registers, 21 KB of shared memory each
+k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tiles, const __grid_constant__ ScoreMaps tmaps,
+         const uint8_t* __restrict__ img_all, uint8_t* __restrict__ S_all, unsigned long long* __restrict__ hitmask, int mask_words) {
     __shared__ __align__(16) uint32_t E[SC_SH][SC_PW];      // E[r][k] = pixels (2k, 2k+1) of staged row r, 16 bits each
     __shared__ __align__(16) uint32_t O[SC_SH][SC_PW];      // O[r][k] = pixels (2k+1, 2k+2)
-    __shared__ uint16_t hard[SC_TW * SC_TH];
+    // the raw rows as the TMA engine delivers them; the survivor queues of step 2 reuse the space once the rows are widened
+    __shared__ __align__(128) uint8_t raw_or_queue[SC_TW * SC_TH * 2];
+    static_assert(SC_SH * SC_RAW <= SC_TW * SC_TH * 2, "raw rows must fit the queue space");
+    __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned long long row_hits[SC_TH];      // bit x of word y: pixel (x0 + x, y0 + y) is a detector hit
     __shared__ __align__(16) uint8_t score_tile[SC_TH][SC_TW];
+    uint8_t* const raw = raw_or_queue;
+    uint16_t* const hard = reinterpret_cast<uint16_t*>(raw_or_queue);
     // grid = (widest layer's tile columns, tile rows of all layers, pairs): no division to find the tile; the blocks
     // beyond a narrower layer's last column leave at once
     const int f = blockIdx.z;
@@ -258,40 +276,74 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     const int w = L.w, h = L.h;
     const uint8_t* img = img_all + L.base + (size_t)f * L.px;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    // ---- stage: item (r, j) = 8 pixels x0-4+8j .. of image row y0-3+r (clamped); pixels outside the row read as 0 - they
-    // are only ever ring pixels of border centres, which are not scored ----
-    const bool word_rows = ((((uintptr_t)img) | (uintptr_t)w) & 3) == 0;      // every staged item then starts on a word of the image
-    auto stage_item = [&](const int r, const int j) {
-        const int gy = min(max(y0 - 3 + r, 0), h - 1);
-        const int gx = x0 - 4 + 8 * j;
-        const uint8_t* p = img + gy * w + gx;
-        uint32_t w0, w1, w2;
-        if (word_rows && gx >= 0 && gx + 12 <= w) {                         // interior of the row: three aligned words
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
-            w0 = q[0]; w1 = q[1]; w2 = q[2];
-        } else if (gx >= w) {                                                // right of the image: nothing to read
-            w0 = w1 = w2 = 0u;
-        } else {
-            w0 = (gx >= 0) ? load4(p) : 0u;
-            w1 = (gx + 4 < w) ? load4(p + 4) : 0u;                          // gx + 4 >= 0 always
-            w2 = (gx + 8 < w) ? load4(p + 8) : 0u;
-        }
-        uint4 ev, od;
-        widen8(w0, w1, w2, ev, od);
-        *reinterpret_cast<uint4*>(&E[r][4 * j]) = ev;
-        *reinterpret_cast<uint4*>(&O[r][4 * j]) = od;
-    };
-    // 38 rows x 9 items, at most two per thread and no index division: the first 32 rows x 8 items are one item per thread,
-    // the remaining 6 rows x 8 items and the ninth item of all 38 rows go to the first 86 threads
-    stage_item(tid >> 3, tid & 7);
-    if (tid < (SC_SH - 32) * 8) stage_item(32 + (tid >> 3), tid & 7);
-    else if (tid < (SC_SH - 32) * 8 + SC_SH) stage_item(tid - (SC_SH - 32) * 8, 8);
+    const int lane = threadIdx.x, wrp = threadIdx.y;
+    // ---- stage: staged row r = image row y0-3+r, staged column c = image column x0-4+c.
+    //  * Layers whose rows are 16-byte aligned in memory (width and base multiples of 16: layers 0, 1 and 3 of 720x576, 82 % of
+    //    the pyramid) are 2-D tensors [F * h][w] to the TMA engine: ONE tensor copy (cp.async.bulk.tensor.2d, SASS UTMALDG)
+    //    brings the 38 x 96-byte box that starts at column x0-16 (a box must start on a 16-byte boundary of memory: measured, an
+    //    unaligned inner coordinate faults as an illegal instruction); coordinates outside the tensor are filled with zeros,
+    //    rows above / below the pair's image are the neighbouring pair's rows.  The threads then widen the raw bytes from
+    //    shared memory.
+    //  * Any other layer: the threads read the rows themselves (aligned words where the layer allows it; one bulk copy per
+    //    row, 38 per tile, measured slower than these loads: 3.02 vs 2.88 ms per 1024 pairs), rows outside the image repeat
+    //    the border row and columns outside read as 0.
+    // What lands outside the image - left of column 0, right of column w-1, above row 0, below row h-1 - is never looked at:
+    // those are only ever ring pixels of border centres, which are not scored. ----
+    const bool boxed = tmaps.use[l] != 0;
+    if (boxed && tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, SC_SH * SC_RAW);
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     :: "r"(smem_addr(raw)), "l"(reinterpret_cast<uint64_t>(&tmaps.map[l])), "r"(x0 - 4 - SC_BOX_X), "r"(f * h + y0 - 3),
+                        "r"(smem_addr(&bar)) : "memory");
+    }
     if (tid < SC_TH) row_hits[tid] = 0ull;
     reinterpret_cast<unsigned long long*>(&score_tile[0][0])[tid] = 0ull;          // 256 threads x 8 bytes = the tile
+    // item (r, j) = the 8 pixels from staged column 8j of row r -> four even-aligned and four odd-aligned 16-bit pairs.
+    // 38 rows x 9 items, at most two per thread and no index division: the first 32 rows x 8 items are one item per thread,
+    // the remaining 6 rows x 8 items and the ninth item of all 38 rows go to the first 86 threads
+    if (boxed) {
+        __syncthreads();                               // the initialised barrier is visible to the waiters
+        mbar_wait(&bar, 0);
+        auto widen_item = [&](const int r, const int j) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(raw + r * SC_RAW + SC_BOX_X) + 2 * j;      // words 3 + 2j .. 5 + 2j of 24
+            uint4 ev, od;
+            widen8(q[0], q[1], q[2], ev, od);
+            *reinterpret_cast<uint4*>(&E[r][4 * j]) = ev;
+            *reinterpret_cast<uint4*>(&O[r][4 * j]) = od;
+        };
+        widen_item(tid >> 3, tid & 7);
+        if (tid < (SC_SH - 32) * 8) widen_item(32 + (tid >> 3), tid & 7);
+        else if (tid < (SC_SH - 32) * 8 + SC_SH) widen_item(tid - (SC_SH - 32) * 8, 8);
+    } else {
+        const bool word_rows = ((((uintptr_t)img) | (uintptr_t)w) & 3) == 0;      // every staged item then starts on a word of the image
+        auto stage_item = [&](const int r, const int j) {
+            const int gy = min(max(y0 - 3 + r, 0), h - 1);
+            const int gx = x0 - 4 + 8 * j;
+            const uint8_t* p = img + gy * w + gx;
+            uint32_t w0, w1, w2;
+            if (word_rows && gx >= 0 && gx + 12 <= w) {                         // interior of the row: three aligned words
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+                w0 = q[0]; w1 = q[1]; w2 = q[2];
+            } else if (gx >= w) {                                                // right of the image: nothing to read
+                w0 = w1 = w2 = 0u;
+            } else {
+                w0 = (gx >= 0) ? load4(p) : 0u;
+                w1 = (gx + 4 < w) ? load4(p + 4) : 0u;                          // gx + 4 >= 0 always
+                w2 = (gx + 8 < w) ? load4(p + 8) : 0u;
+            }
+            uint4 ev, od;
+            widen8(w0, w1, w2, ev, od);
+            *reinterpret_cast<uint4*>(&E[r][4 * j]) = ev;
+            *reinterpret_cast<uint4*>(&O[r][4 * j]) = od;
+        };
+        stage_item(tid >> 3, tid & 7);
+        if (tid < (SC_SH - 32) * 8) stage_item(32 + (tid >> 3), tid & 7);
+        else if (tid < (SC_SH - 32) * 8 + SC_SH) stage_item(tid - (SC_SH - 32) * 8, 8);
+    }
     __syncthreads();
     // ---- step 1: a thread owns the centre pairs (x0 + 2 lane, +1) of rows y0 + ty + 8 jy; staged column of the pair's first
     // pixel is 4 + 2 lane = word 2 + lane of E ----
-    const int lane = threadIdx.x, wrp = threadIdx.y;
     const int xa = x0 + 2 * lane;
     const bool in_lo = xa >= 3 && xa < w - 3, in_hi = xa + 1 >= 3 && xa + 1 < w - 3;
     uint32_t mine = 0;                                  // bit 2 * jy + half: that pixel needs the full score
@@ -358,19 +410,19 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
         if (sc >= BRISK_THRESHOLD) atomicOr(reinterpret_cast<unsigned*>(&row_hits[ly]) + (lx >> 5), 1u << (lx & 31));   // native 32-bit shared atomic
     }
     __syncthreads();
-    // the score tile, 8 bytes per thread
+    // the score tile, 8 bytes per thread: one 64-bit store where the layer's rows allow it, else two words, else bytes
     {
         const int ry = tid >> 3, cx = (tid & 7) * 8;
         const int y = y0 + ry;
         if (y < h) {
             uint8_t* dst = S_all + L.base + (size_t)f * L.px + (size_t)y * w + x0 + cx;
-            const bool words = (((uintptr_t)dst | (uintptr_t)w) & 3) == 0;     // odd frame sizes shift the layer bases
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(&score_tile[ry][cx]);
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const int x = x0 + cx + 4 * half;
-                if (words && x + 4 <= w) *reinterpret_cast<uint32_t*>(dst + 4 * half) = src[half];
-                else for (int j = 0; j < 4; j++) if (x + j < w) dst[4 * half + j] = score_tile[ry][cx + 4 * half + j];
+            const uint2 v = *reinterpret_cast<const uint2*>(&score_tile[ry][cx]);
+            const uint32_t a = (uint32_t)(uintptr_t)dst;                        // odd frame sizes shift the layer bases and rows
+            if (x0 + cx + 8 <= w && (a & 3u) == 0) {
+                if ((a & 7u) == 0) *reinterpret_cast<uint2*>(dst) = v;
+                else { reinterpret_cast<uint32_t*>(dst)[0] = v.x; reinterpret_cast<uint32_t*>(dst)[1] = v.y; }
+            } else {
+                for (int j = 0; j < 8; j++) if (x0 + cx + j < w) dst[j] = score_tile[ry][cx + j];
             }
         }
     }
@@ -383,7 +435,50 @@ int score_mask_words(int frame_width) { return (frame_width + SC_TW - 1) / SC_TW
 int score_tile_rows(const int lh[N_LAYERS]) { int r = 0; for (int l = 0; l < N_LAYERS; l++) r += (lh[l] + SC_TH - 1) / SC_TH; return r; }
 int score_tile_rows_max() { return (int)(sizeof(ScoreTiles::layer) / sizeof(uint8_t)); }
 
-void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* S, unsigned long long* hitmask) {
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup: the library does not link libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (getenv("MFK_SCORES_NO_TENSOR_MAP")) return (EncodeTiledFn) nullptr;       // A/B measurements: thread loads everywhere
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (EncodeTiledFn) nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// The tensor maps describe the lane's pyramid buffer for one batch size (the layer bases depend on F): rebuilt when either
+// changes, i.e. practically once per lane.  A layer without 16-byte aligned rows (or a driver without the entry point) keeps
+// use = 0 and is staged by the threads' own loads.
+static void refresh_score_maps(ScoreMapCache& cache, const Geom& g, const uint8_t* img) {
+    if (cache.F == g.F && cache.img == img) return;
+    ScoreMaps& sm = *reinterpret_cast<ScoreMaps*>(cache.blob);
+    memset(&sm, 0, sizeof(sm));
+    EncodeTiledFn enc = encode_tiled();
+    for (int l = 0; l < N_LAYERS && enc; l++) {
+        const LayerGeom& L = g.L[l];
+        const uintptr_t base = (uintptr_t)(img + L.base);
+        if ((L.w & 15) || (base & 15) || L.w < 16) continue;
+        const cuuint64_t dims[2] = {(cuuint64_t)L.w, (cuuint64_t)L.h * (cuuint64_t)g.F};
+        const cuuint64_t strides[1] = {(cuuint64_t)L.w};
+        const cuuint32_t box[2] = {(cuuint32_t)SC_RAW, (cuuint32_t)SC_SH};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult rc = enc(&sm.map[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        sm.use[l] = rc == CUDA_SUCCESS;
+    }
+    cache.F = g.F; cache.img = img;
+}
+
+void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* S, unsigned long long* hitmask, ScoreMapCache& cache) {
     ScoreTiles tiles;
     int rows = 0, widest = 0;
     for (int l = 0; l < N_LAYERS; l++) {
@@ -391,8 +486,10 @@ void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* 
         widest = max(widest, tiles.across[l]);
         for (int y = 0; y < g.L[l].h && rows < 768; y += SC_TH, rows++) { tiles.layer[rows] = (uint8_t)l; tiles.y0[rows] = (int16_t)y; }
     }
+    refresh_score_maps(cache, g, img);
     // gridDim.z <= 65535 pairs per launch sequence (context.cu caps max_pairs far below)
-    k_scores<<<dim3(widest, rows, g.F), dim3(32, 8), 0, st>>>(g, tiles, img, S, hitmask, score_mask_words(g.W));
+    k_scores<<<dim3(widest, rows, g.F), dim3(32, 8), 0, st>>>(g, tiles, *reinterpret_cast<const ScoreMaps*>(cache.blob), img, S, hitmask,
+                                                               score_mask_words(g.W));
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -7,6 +7,8 @@
 // Lanes own receptive fields (43 box means from the integral image), orientation pairs, pair tests and SSD
 // tests; bits are packed with __ballot_sync, whose lane order is laid out so that the ballot words ARE the
 // descriptor bytes.  Compiled with -fmad=false: the orientation angle must round exactly as on the host.
+#include <stdlib.h>
+
 #include "brisk_device.cuh"
 #include "desc_device.cuh"
 
@@ -22,6 +24,9 @@ constexpr int PATCH_PAD = 368;        // 19 x 19 = 361 patch bytes, padded
 constexpr int ROI_MAX = 32;           // regions of interest up to this side are staged in shared memory
 constexpr int ROI_WORDS = 9;          // aligned 32-bit words that cover 32 columns from any byte offset
 constexpr int ROI_STRIDE = 4 * ROI_WORDS + 4;    // bytes per staged row (40: keeps rows 8-byte aligned)
+
+// one receptive field of the pattern table: 16 bytes, one 128-bit read-only load
+__device__ __forceinline__ float4 load_point(const FreakPoint* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 struct WarpScratch {
     alignas(16) uint8_t roi[2][ROI_MAX * ROI_STRIDE];
@@ -135,7 +140,7 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpScratch& ws = scratch[wib];
     const uint32_t n_rows = cb.keep_scan[cb.live[0]];
-    const uint32_t rows_base = cb.live[3];                         // saved by k_advance, which already ran for this batch
+    const uint32_t rows_base = cb.live[3];                         // saved by the advance step (k_scatter_rows), which already ran for this batch
     const int W1 = g.W + 1;
     const size_t ipx = (size_t)W1 * (g.H + 1);
     // rows differ a lot in cost (region staged or not, pattern scale), so warps draw row tickets instead of striding; the
@@ -146,7 +151,7 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
         if (r >= n_rows) break;
         uint32_t next = 0;
         if (lane == 0) next = first_dynamic + atomicAdd(&cb.live[2], 1u);
-        if (rows_base + r >= (uint32_t)g.row_cap) break;            // overflow is flagged by k_advance
+        if (rows_base + r >= (uint32_t)g.row_cap) break;            // overflow is flagged by the advance step
         const uint32_t c = cb.row_src[r];
         const int f = cb.meta[c] >> 3;
         const float kx = cb.kx[c], ky = cb.ky[c], ksize = cb.ksize[c];
@@ -164,7 +169,7 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
 
         // --- FREAK: orientation from the unrotated pattern ---
         const FreakPoint* P0 = tb.points + (size_t)sidx * FREAK_ORIENTATIONS * FREAK_POINTS;
-        for (int p = lane; p < FREAK_POINTS; p += 32) ws.field[0][p] = (uint8_t)mean_intensity(I, W1, P0[p], kx, ky);
+        for (int p = lane; p < FREAK_POINTS; p += 32) { const float4 P = load_point(P0 + p); ws.field[0][p] = (uint8_t)mean_intensity(I, W1, P.x, P.y, P.z, kx, ky); }
         __syncwarp();
         int d0 = 0, d1 = 0;
         for (int q = lane; q < FREAK_ORIENT_PAIRS; q += 32) {
@@ -179,7 +184,7 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
 
         // --- FREAK: the 64 pair tests the reference keeps ---
         const FreakPoint* PT = P0 + (size_t)theta * FREAK_POINTS;
-        for (int p = lane; p < FREAK_POINTS; p += 32) ws.field[1][p] = (uint8_t)mean_intensity(I, W1, PT[p], kx, ky);
+        for (int p = lane; p < FREAK_POINTS; p += 32) { const float4 P = load_point(PT + p); ws.field[1][p] = (uint8_t)mean_intensity(I, W1, P.x, P.y, P.z, kx, ky); }
         __syncwarp();
         uint32_t app[2];
 #pragma unroll
@@ -216,6 +221,7 @@ void launch_describe(cudaStream_t st, const Geom& g, const uint8_t* store, int s
         int per_sm = 0, sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_describe, DW * 32, 0);
+        if (const char* e = getenv("MFK_DESC_BLOCKS")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // measurements
         blocks = max(1, per_sm) * max(1, sms);
     }
     k_describe<<<blocks, DW * 32, 0, st>>>(g, store, store_frames, pl, integral, cb, tb, (RowOut*)rows);

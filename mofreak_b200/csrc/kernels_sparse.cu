@@ -12,6 +12,7 @@
 //            decided completely (scans above/below, refinement, keypoint record);
 //   phase B  one block per pair: the few candidates with ties, layer by layer, by a fixed point whose only
 //            ordering requirement is "every raster-earlier undecided tie candidate within 3 px is final".
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "sparse_device.cuh"
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_pa_test(const __grid_constant__ 
     }
 }
 
-__global__ void __launch_bounds__(PA_THREADS) k_pa_above(const __grid_constant__ Geom g, Maps m, CandBuf cb) {
+__global__ void __launch_bounds__(PA_THREADS, 10) k_pa_above(const __grid_constant__ Geom g, Maps m, CandBuf cb) {
     const uint32_t n = min(cb.q_count[0], cb.q_cap);
     const uint32_t n_round = (n + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_pa_above(const __grid_constant__
     }
 }
 
-__global__ void __launch_bounds__(PA_THREADS) k_pa_below(const __grid_constant__ Geom g, Maps m, CandBuf cb) {
+__global__ void __launch_bounds__(PA_THREADS, 10) k_pa_below(const __grid_constant__ Geom g, Maps m, CandBuf cb) {
     const uint32_t n = min(cb.q_count[1], cb.q_cap);
     const uint32_t n_round = (n + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
@@ -144,12 +145,27 @@ __global__ void __launch_bounds__(PA_THREADS) k_pa_emit(const __grid_constant__ 
     }
 }
 
+// blocks per SM of the four kernels (MFK_PA_BLOCKS="t,a,b,e" overrides, for measurements)
+static const int* pa_blocks() {
+    static int b[4] = {8, 8, 8, 8};
+    static bool parsed = false;
+    if (!parsed) {
+        parsed = true;
+        if (const char* e = getenv("MFK_PA_BLOCKS")) {
+            int v[4];
+            if (sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+                for (int i = 0; i < 4; i++) if (v[i] >= 1 && v[i] <= 16) b[i] = v[i];
+        }
+    }
+    return b;
+}
+
 void launch_phase_a(cudaStream_t st, const Geom& g, Maps m, CandBuf cb, DeviceTables tb) {
-    const int grid = 148 * 8;
-    k_pa_test<<<grid, PA_THREADS, 0, st>>>(g, m, cb);
-    k_pa_above<<<grid, PA_THREADS, 0, st>>>(g, m, cb);
-    k_pa_below<<<grid, PA_THREADS, 0, st>>>(g, m, cb);
-    k_pa_emit<<<grid, PA_THREADS, 0, st>>>(g, m, cb, tb);
+    const int* b = pa_blocks();
+    k_pa_test<<<148 * b[0], PA_THREADS, 0, st>>>(g, m, cb);
+    k_pa_above<<<148 * b[1], PA_THREADS, 0, st>>>(g, m, cb);
+    k_pa_below<<<148 * b[2], PA_THREADS, 0, st>>>(g, m, cb);
+    k_pa_emit<<<148 * b[3], PA_THREADS, 0, st>>>(g, m, cb, tb);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -344,10 +360,24 @@ void launch_keep_flags(cudaStream_t st, const Geom& g, CandBuf cb) {
 namespace mfk {
 
 // after the scan of the keep flags: row r of the batch comes from candidate row_src[r]; rows of pair f are the
-// kept candidates between the pair's first and one-past-last candidate
+// kept candidates between the pair's first and one-past-last candidate.  One thread also performs the one serialised step
+// between batches: this batch's base in the shared row accumulation, counters advanced (nothing in this kernel reads what
+// that step writes; the descriptor kernel, launched next, does).
 __global__ void k_scatter_rows(Geom g, CandBuf cb, uint32_t* __restrict__ pair_rows) {
     const uint32_t n = cb.live[0];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    if (tid == 0) {
+        const uint32_t rows = cb.keep_scan[n];
+        const uint32_t have = cb.counters[1];
+        cb.live[3] = have;              // rows_base of this batch for k_describe
+        cb.live[2] = 0;                 // fresh row tickets for k_describe
+        // overflow seen by this batch's lane-private kernels joins the shared flags here, behind any row reset
+        if (cb.live[1]) { cb.counters[0] |= cb.live[1]; cb.live[1] = 0; }
+        if (have + rows > (uint32_t)g.row_cap) { cb.counters[0] |= 2u; cb.counters[1] = (uint32_t)g.row_cap; }
+        else cb.counters[1] = have + rows;
+        cb.counters[2] += (uint32_t)g.F;
+        cb.counters[3] = n;
+    }
     for (uint32_t i = tid; i < n; i += nthreads)
         if (cb.flags[i] & ST_KEEP) cb.row_src[cb.keep_scan[i]] = i;
     for (uint32_t i = tid; i < (uint32_t)g.F; i += nthreads) {
@@ -359,21 +389,5 @@ __global__ void k_scatter_rows(Geom g, CandBuf cb, uint32_t* __restrict__ pair_r
 void launch_scatter_rows(cudaStream_t st, const Geom& g, CandBuf cb, uint32_t* pair_rows) {
     k_scatter_rows<<<148 * 8, 256, 0, st>>>(g, cb, pair_rows);
 }
-
-// the one serialised step between batches: this batch's base in the shared row accumulation, counters advanced
-__global__ void k_advance(Geom g, CandBuf cb) {
-    const uint32_t rows = cb.keep_scan[cb.live[0]];
-    const uint32_t have = cb.counters[1];
-    cb.live[3] = have;              // rows_base of this batch for k_describe
-    cb.live[2] = 0;                 // fresh row tickets for k_describe
-    // overflow seen by this batch's lane-private kernels joins the shared flags here, behind any row reset
-    if (cb.live[1]) { cb.counters[0] |= cb.live[1]; cb.live[1] = 0; }
-    if (have + rows > (uint32_t)g.row_cap) { cb.counters[0] |= 2u; cb.counters[1] = (uint32_t)g.row_cap; }
-    else cb.counters[1] = have + rows;
-    cb.counters[2] += (uint32_t)g.F;
-    cb.counters[3] = cb.live[0];
-}
-
-void launch_advance(cudaStream_t st, const Geom& g, CandBuf cb) { k_advance<<<1, 1, 0, st>>>(g, cb); }
 
 }  // namespace mfk

@@ -178,7 +178,7 @@ int scale_index_from_table(float kp_size) {
 const Tables& tables() {
     std::call_once(g_once, [] {
         Tables* T = new Tables();
-        T->points = new FreakPoint[(size_t)FREAK_SCALES * FREAK_ORIENTATIONS * FREAK_POINTS];
+        T->points = new FreakPoint[(size_t)FREAK_SCALES * FREAK_ORIENTATIONS * FREAK_POINTS]();
         fill_points(*T);
         fill_orientation_pairs(*T);
         fill_used_pairs(*T);

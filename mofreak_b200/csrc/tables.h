@@ -15,7 +15,7 @@ enum {
     FREAK_USED_PAIRS = 64,     // the reference keeps descriptor bytes 0..7 only (MoFREAKUtilities.cpp:453-456)
 };
 
-struct FreakPoint { float x, y, sigma; };          // offset from the keypoint and box half-size
+struct alignas(16) FreakPoint { float x, y, sigma, pad; };   // offset from the keypoint and box half-size; one 128-bit load
 struct OrientPair { int16_t i, j; int32_t wdx, wdy; };
 struct UsedPair   { uint8_t i, j; };               // index = byte*8 + bit of the 8 appearance bytes
 

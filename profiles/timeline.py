@@ -23,4 +23,4 @@ ms = ctx.timer_stop()
 tl = ctx.profile_timeline()
 print("total_ms", ms, "spans", len(tl))
 for i, (name, a, b) in enumerate(tl):
-    print("%4d batch %2d %-16s %8.3f %8.3f %7.3f" % (i, i // 10, name, a, b, b - a))
+    print("%4d batch %2d %-16s %8.3f %8.3f %7.3f" % (i, i // 11, name, a, b, b - a))
