@@ -102,6 +102,7 @@ struct mfk_ctx {
     bool main_wait_pending = false;       // the next launch sequence orders its shared-row part after main_mark
     bool serial = false;
     bool prioritised = true;              // MFK_PRIORITY=0: one stream per lane (plus the integral side stream), no priorities
+    bool tail_overlap = false;            // MFK_TAIL_OVERLAP=1: descriptor kernels of consecutive batches may overlap
     bool early_compact = true;            // MFK_EARLY_COMPACT=0: the whole second compaction waits for the previous tail
     bool fused_front = true;              // MFK_FUSED_FRONT=0 forces the separate dense kernels (A/B measurements, wide frames use them anyway)
     uint64_t batches = 0;
@@ -114,7 +115,7 @@ struct mfk_ctx {
     uint32_t* pair_rows = nullptr;
     size_t pair_cap = 0, pairs_queued = 0;
     DeviceTables tb{};
-    void* tb_alloc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* tb_alloc[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint8_t* codebook = nullptr;
     int K = 0;
     uint32_t* bow_counts = nullptr;
@@ -227,6 +228,17 @@ int upload_tables(mfk_ctx* c) {
     CU(c, dalloc(&mn, 2 * 361)); c->tb_alloc[5] = mn;
     CU(c, cudaMemcpy(mn, T.mip_needed, sizeof T.mip_needed, cudaMemcpyHostToDevice));
     c->tb.mip_needed = mn; c->tb.n_mip_needed = T.n_mip_needed;
+    {
+        uint32_t plan[2 * 361];
+        for (int i = 0; i < T.n_mip_needed; i++) {
+            const uint32_t e = T.mip_needed[i], fr = e >> 15, dx = e & 31, dy = (e >> 5) & 31;
+            plan[i] = describe_patch_offset((int)fr, (int)dx, (int)dy) | (16u * dx) << 10 | (16u * dy) << 19 | fr << 28;
+        }
+        uint32_t* mp;
+        CU(c, dalloc(&mp, 2 * 361)); c->tb_alloc[6] = mp;
+        CU(c, cudaMemcpy(mp, plan, sizeof(uint32_t) * T.n_mip_needed, cudaMemcpyHostToDevice));
+        c->tb.mip_plan = mp;
+    }
     c->tb.points = pts; c->tb.pattern_size = ps; c->tb.scale_threshold = thr; c->tb.orient = op; c->tb.used = up;
     return MFK_OK;
 }
@@ -296,7 +308,7 @@ int run_batch(mfk_ctx* c, const int32_t* cur, const int32_t* prev, const int32_t
     mfk_ctx::Lane& P = c->lane[c->last_lane];            // lane of the previous batch
     cudaStream_t st = L.stream;
     PairList pl{L.pairs, L.pairs + c->max_pairs, L.pairs + 2 * (size_t)c->max_pairs};
-    c->launches += launch_set_pairs(st, cur, prev, label, F, pl);
+    c->launches += launch_set_pairs(st, cur, prev, label, F, c->store_frames, pl);
     // write-back marks only ever land on layers 1..5 (they come from scans issued from the layer below), so layer 0's
     // share of the map stays zero as long as the lane keeps its geometry
     if (L.seen_F == F) CU(c, cudaMemsetAsync(L.maps.seen + g.L[1].base, 0, (size_t)F * g.pyr_px - g.L[1].base, st));
@@ -349,11 +361,12 @@ int run_batch(mfk_ctx* c, const int32_t* cur, const int32_t* prev, const int32_t
     if (!c->early_compact) keep_scan();
     // kept keypoints -> row slots of this batch, per-pair row counts, and this batch's base in the shared accumulation
     { Span s(c, P_COMPACT, 1, st);   launch_scatter_rows(st, g, L.cb, c->pair_rows + first); }
+    if (c->tail_overlap) CU(c, cudaEventRecord(L.advanced, st));       // the next batch's tail may start under this descriptor kernel
     if (!c->serial) CU(c, cudaStreamWaitEvent(st, L.aux_join, 0));
     { Span s(c, P_DESCRIBE, 1, st);
       launch_describe(st, g, c->store, c->store_frames, pl, L.maps.img, L.integral, L.cb, c->tb, c->rows_buf);
     }
-    CU(c, cudaEventRecord(L.advanced, st));
+    if (!c->tail_overlap) CU(c, cudaEventRecord(L.advanced, st));
     CU(c, cudaGetLastError());
     L.used = true;
     c->last = g; c->have_last = true; c->last_lane = li;
@@ -494,6 +507,7 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     if (const char* e = getenv("MFK_FUSED_FRONT")) c->fused_front = atoi(e) != 0;
     if (const char* e = getenv("MFK_PRIORITY")) c->prioritised = atoi(e) != 0;
     if (const char* e = getenv("MFK_EARLY_COMPACT")) c->early_compact = atoi(e) != 0;
+    if (const char* e = getenv("MFK_TAIL_OVERLAP")) c->tail_overlap = atoi(e) != 0;
     int prio_low = 0, prio_high = 0;
     CUC(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
     for (int li = 0; li < c->lanes_built; li++) {

@@ -96,10 +96,18 @@ __device__ __forceinline__ int mean_intensity(const int32_t* __restrict__ I, int
     const int y_top = round_half_up_nonneg(yf - radius, 0);
     const int x_right = round_half_up_nonneg(xf + radius, 1);
     const int y_bottom = round_half_up_nonneg(yf + radius, 1);
+#ifdef __CUDA_ARCH__
+    // read-only global loads spelled out: the kernel keeps the pair's base pointer opaque, which would otherwise make these generic
+    const int v = __ldg(I + (y_bottom * W1 + x_right)) - __ldg(I + (y_bottom * W1 + x_left)) + __ldg(I + (y_top * W1 + x_left)) -
+                  __ldg(I + (y_top * W1 + x_right));
+#else
     const int v = I[y_bottom * W1 + x_right] - I[y_bottom * W1 + x_left] + I[y_top * W1 + x_left] - I[y_top * W1 + x_right];
+#endif
     const int area = (x_right - x_left) * (y_bottom - y_top);
 #ifdef __CUDA_ARCH__
-    int q = (int)__fdividef((float)v, (float)area);
+    float rcp;                                  // one MUFU.RCP: 1 <= area < 2^17 needs none of __fdividef's range scaling
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"((float)area));
+    int q = (int)((float)v * rcp);
 #else
     int q = (int)((float)v / (float)area);
 #endif

@@ -54,13 +54,15 @@ struct DeviceTables {             // device copies of mfk::Tables
     const UsedPair* used;             // [64]
     const uint16_t* mip_needed;       // patch pixels the MIP tests read (tables.h)
     int n_mip_needed;
+    const uint32_t* mip_plan;         // the same pixels as the descriptor kernel's resize loop wants them: byte offset of the pixel in
+                                      // the warp's [current | previous] patch buffers (10 bits) | 16 * column << 10 | 16 * row << 19 | frame << 28
 };
 
 // --- dense stage ------------------------------------------------------------------------------------
 // interleaved BGR -> gray as cv::cvtColor computes it (coeff_bits 14: OpenCV 2.4, 15: OpenCV >= 3)
 void launch_bgr2gray(cudaStream_t, const uint8_t* bgr, uint8_t* gray, size_t n_px, int coeff_bits);
 // pair descriptions travel as kernel parameters (no staging copy, no host stall): 256 per launch; returns launches made
-int launch_set_pairs(cudaStream_t, const int32_t* cur_host, const int32_t* prev_host, const int32_t* label_host, int n, PairList dst);
+int launch_set_pairs(cudaStream_t, const int32_t* cur_host, const int32_t* prev_host, const int32_t* label_host, int n, int store_frames, PairList dst);   // slots land reduced modulo the store size
 void launch_absdiff(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, uint8_t* img);
 void launch_pyramid(cudaStream_t, const Geom&, uint8_t* img);                                  // layers 1..5
 int  score_mask_words(int frame_width);        // 64-bit hit-mask words per (pair, layer row)
@@ -94,6 +96,8 @@ void launch_keep_flags(cudaStream_t, const Geom&, CandBuf);           // flags -
 void launch_scatter_rows(cudaStream_t, const Geom&, CandBuf, uint32_t* pair_rows);   // after the scan: row_src, per-pair counts (pair_rows = this batch's slice)
 void launch_describe(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, const uint8_t* img,
                      const int32_t* integral, CandBuf, DeviceTables, void* rows /*mfk_row*/);
+// byte offset of patch pixel (column dx, row dy) of frame fr (0 current, 1 previous) in a warp's patch buffers (kernels_desc.cu)
+uint32_t describe_patch_offset(int fr, int dx, int dy);
 void launch_mip_only(cudaStream_t, int W, int H, const uint8_t* cur, const uint8_t* prev, const float* kp_xys, int n,
                      uint8_t* motion, uint32_t* err_flag, DeviceTables);
 // --- bag of words --------------------------------------------------------------------------------------

@@ -24,8 +24,8 @@ namespace mfk {
 __global__ void k_absdiff(const uint8_t* __restrict__ store, int store_frames, const int32_t* __restrict__ cur_slot,
                           const int32_t* __restrict__ prev_slot, uint8_t* __restrict__ img, int px, int vec_ok) {
     const int f = blockIdx.y;
-    const uint8_t* a = store + (size_t)(cur_slot[f] % store_frames) * px;
-    const uint8_t* b = store + (size_t)(prev_slot[f] % store_frames) * px;
+    const uint8_t* a = store + (size_t)cur_slot[f] * px;            // slots arrive reduced modulo the store size (launch_set_pairs)
+    const uint8_t* b = store + (size_t)prev_slot[f] * px;
     uint8_t* d = img + (size_t)f * px;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
@@ -100,12 +100,14 @@ __global__ void k_set_pairs(const __grid_constant__ PairChunk ch, int n, int32_t
     if (i < n) { cur[i] = ch.cur[i]; prev[i] = ch.prev[i]; label[i] = ch.label[i]; }
 }
 
-int launch_set_pairs(cudaStream_t st, const int32_t* cur, const int32_t* prev, const int32_t* label, int n, PairList dst) {
+// (slots are reduced modulo the store size here, once per pair: the kernels index the store with them as they are)
+int launch_set_pairs(cudaStream_t st, const int32_t* cur, const int32_t* prev, const int32_t* label, int n, int store_frames, PairList dst) {
     int launches = 0;
     PairChunk ch;
     for (int done = 0; done < n; done += 256, launches++) {
         const int m = min(256, n - done);
-        memcpy(ch.cur, cur + done, (size_t)m * 4); memcpy(ch.prev, prev + done, (size_t)m * 4); memcpy(ch.label, label + done, (size_t)m * 4);
+        for (int i = 0; i < m; i++) { ch.cur[i] = cur[done + i] % store_frames; ch.prev[i] = prev[done + i] % store_frames; }
+        memcpy(ch.label, label + done, (size_t)m * 4);
         k_set_pairs<<<1, 256, 0, st>>>(ch, m, const_cast<int32_t*>(dst.cur_slot) + done, const_cast<int32_t*>(dst.prev_slot) + done,
                                        const_cast<int32_t*>(dst.label) + done);
     }

@@ -7,6 +7,7 @@
 // Lanes own receptive fields (43 box means from the integral image), orientation pairs, pair tests and SSD
 // tests; bits are packed with __ballot_sync, whose lane order is laid out so that the ballot words ARE the
 // descriptor bytes.  Compiled with -fmad=false: the orientation angle must round exactly as on the host.
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "brisk_device.cuh"
@@ -53,28 +54,30 @@ __device__ __forceinline__ void roi_stage(WarpScratch& ws, const uint8_t* __rest
     uint8_t* s0 = &ws.roi[0][rl * ROI_STRIDE + 4 * k];
     uint8_t* s1 = &ws.roi[1][rl * ROI_STRIDE + 4 * k];
     const bool col = k < nw;
-    for (int r = rl; r < s; r += 4) {
-        if (col) {
-            if (async) {
+    // two copies of the loop: one branch on `async` inside it becomes predicated code that issues both bodies
+    if (async) {
+        if (col)
+            for (int r = rl; r < s; r += 4) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(s0)), "l"(c) : "memory");
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(s1)), "l"(p) : "memory");
-            } else {
+                c += (size_t)4 * W; p += (size_t)4 * W; s0 += 4 * ROI_STRIDE; s1 += 4 * ROI_STRIDE;
+            }
+        if (nw == 9 && lane < s) {
+            const size_t off = org + (size_t)lane * W + 32;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(&ws.roi[0][lane * ROI_STRIDE + 32])), "l"(cur + off));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(&ws.roi[1][lane * ROI_STRIDE + 32])), "l"(prev + off));
+        }
+    } else {
+        if (col)
+            for (int r = rl; r < s; r += 4) {
                 *reinterpret_cast<uint32_t*>(s0) = load4(c);
                 *reinterpret_cast<uint32_t*>(s1) = load4(p);
+                c += (size_t)4 * W; p += (size_t)4 * W; s0 += 4 * ROI_STRIDE; s1 += 4 * ROI_STRIDE;
             }
-        }
-        c += (size_t)4 * W; p += (size_t)4 * W; s0 += 4 * ROI_STRIDE; s1 += 4 * ROI_STRIDE;
-    }
-    if (nw == 9 && lane < s) {
-        const size_t off = org + (size_t)lane * W + 32;
-        uint8_t* e0 = &ws.roi[0][lane * ROI_STRIDE + 32];
-        uint8_t* e1 = &ws.roi[1][lane * ROI_STRIDE + 32];
-        if (async) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(e0)), "l"(cur + off));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(e1)), "l"(prev + off));
-        } else {
-            *reinterpret_cast<uint32_t*>(e0) = load4(cur + off);
-            *reinterpret_cast<uint32_t*>(e1) = load4(prev + off);
+        if (nw == 9 && lane < s) {
+            const size_t off = org + (size_t)lane * W + 32;
+            *reinterpret_cast<uint32_t*>(&ws.roi[0][lane * ROI_STRIDE + 32]) = load4(cur + off);
+            *reinterpret_cast<uint32_t*>(&ws.roi[1][lane * ROI_STRIDE + 32]) = load4(prev + off);
         }
     }
     if (async) asm volatile("cp.async.commit_group;");
@@ -97,23 +100,31 @@ __device__ __forceinline__ void resize_roi_pair(WarpScratch& ws, const uint8_t* 
         ws.ctap[lane] = col_tap(t, s, staged ? (tl_x & 3) : 0);
     }
     __syncwarp();
-    // only the 276 of the 2 x 361 patch pixels that the SSD tests read are interpolated.  Two copies of the loop so that
-    // the staged one reads through shared-memory loads (a pointer that may be either space costs generic loads)
+    // only the 276 of the 2 x 361 patch pixels that the SSD tests read are interpolated, in the order of tb.mip_plan, whose
+    // entries carry the byte offsets of the pixel's destination and of its row / column taps.  Two copies of the loop so
+    // that the staged one reads through shared-memory loads (a pointer that may be either space costs generic loads)
+    uint8_t* const patch = ws.cur;                                  // cur and prev are adjacent: prev = cur + PATCH_PAD
+    const char* const rt = reinterpret_cast<const char*>(ws.rtap);
+    const char* const ct = reinterpret_cast<const char*>(ws.ctap);
     if (staged) {
         for (int i = lane; i < tb.n_mip_needed; i += 32) {
-            const int e = tb.mip_needed[i];
-            const int fr = e >> 15, dx = e & 31, dy = (e >> 5) & 31;
-            const int v = resize_px_flat(ws.roi[fr], ws.rtap[dy], ws.ctap[dx]);
-            (fr ? ws.prev : ws.cur)[dy * PATCH + dx] = (uint8_t)v;
+            const uint32_t e = __ldg(tb.mip_plan + i);
+            const int4 ry = *reinterpret_cast<const int4*>(rt + ((e >> 19) & 0x1ffu));      // 128-bit shared loads (the taps are 16-byte aligned)
+            const int4 cx = *reinterpret_cast<const int4*>(ct + ((e >> 10) & 0x1ffu));
+            const RowTap ty{ry.x, ry.y, ry.z, ry.w};
+            const ColTap tx{cx.x, cx.y, cx.z, cx.w};
+            patch[e & 0x3ffu] = (uint8_t)resize_px_flat(ws.roi[0] + (e >> 28) * (ROI_MAX * ROI_STRIDE), ty, tx);
         }
     } else {
         const uint8_t* src0 = cur + (size_t)tl_y * W + tl_x;
         const uint8_t* src1 = prev + (size_t)tl_y * W + tl_x;
         for (int i = lane; i < tb.n_mip_needed; i += 32) {
-            const int e = tb.mip_needed[i];
-            const int fr = e >> 15, dx = e & 31, dy = (e >> 5) & 31;
-            const int v = resize_px_flat(fr ? src1 : src0, ws.rtap[dy], ws.ctap[dx]);
-            (fr ? ws.prev : ws.cur)[dy * PATCH + dx] = (uint8_t)v;
+            const uint32_t e = __ldg(tb.mip_plan + i);
+            const int4 ry = *reinterpret_cast<const int4*>(rt + ((e >> 19) & 0x1ffu));      // 128-bit shared loads (the taps are 16-byte aligned)
+            const int4 cx = *reinterpret_cast<const int4*>(ct + ((e >> 10) & 0x1ffu));
+            const RowTap ty{ry.x, ry.y, ry.z, ry.w};
+            const ColTap tx{cx.x, cx.y, cx.z, cx.w};
+            patch[e & 0x3ffu] = (uint8_t)resize_px_flat((e >> 28) ? src1 : src0, ty, tx);
         }
     }
     __syncwarp();
@@ -150,17 +161,22 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
     for (;;) {
         if (r >= n_rows) break;
         uint32_t next = 0;
-        if (lane == 0) next = first_dynamic + atomicAdd(&cb.live[2], 1u);
+        if (lane == 0) {              // plain atom: the compiler wraps atomicAdd in a warp-aggregation sequence (~35 instructions per row)
+            uint32_t t;
+            asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(cb.live + 2) : "memory");
+            next = first_dynamic + t;
+        }
         if (rows_base + r >= (uint32_t)g.row_cap) break;            // overflow is flagged by the advance step
         const uint32_t c = cb.row_src[r];
         const int f = cb.meta[c] >> 3;
         const float kx = cb.kx[c], ky = cb.ky[c], ksize = cb.ksize[c];
         const int sidx = cb.scale_idx[c];
         const int32_t* I = integral + (size_t)f * ipx;
+        asm volatile("" : "+l"(I));     // keep the pair's base in a register pair: folded into every gather it costs 64-bit adds with carries
 
         // --- MIP geometry first: the two regions of interest start travelling to shared memory now and are needed last ---
-        const uint8_t* cur = store + (size_t)(pl.cur_slot[f] % store_frames) * g.L[0].px;
-        const uint8_t* prev = store + (size_t)(pl.prev_slot[f] % store_frames) * g.L[0].px;
+        const uint8_t* cur = store + (size_t)pl.cur_slot[f] * g.L[0].px;
+        const uint8_t* prev = store + (size_t)pl.prev_slot[f] * g.L[0].px;
         const int xi = (int)kx, yi = (int)ky;                          // float -> int at the call, :460
         const int half = (int)ksize / 2;
         const int side = (int)ceilf(ksize);
@@ -208,6 +224,11 @@ k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, in
         r = __shfl_sync(0xffffffffu, next, 0);
     }
 }
+
+static_assert(offsetof(WarpScratch, prev) == offsetof(WarpScratch, cur) + PATCH_PAD, "the patch buffers are adjacent");
+static_assert(2 * PATCH_PAD <= 1024 && 16 * PATCH <= 512, "mip_plan field widths");
+
+uint32_t describe_patch_offset(int fr, int dx, int dy) { return (uint32_t)(fr * PATCH_PAD + dy * PATCH + dx); }
 
 void launch_describe(cudaStream_t st, const Geom& g, const uint8_t* store, int store_frames, PairList pl, const uint8_t*,
                      const int32_t* integral, CandBuf cb, DeviceTables tb, void* rows) {

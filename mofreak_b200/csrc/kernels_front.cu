@@ -171,8 +171,8 @@ k_front(const __grid_constant__ Geom g, const __grid_constant__ FrontLayout fl, 
     uint8_t* A = sm + fl.off[0];
     uint8_t* B = sm + fl.off_prev;
     const int p0 = fl.pitch[0];
-    const uint8_t* cur = store + (size_t)(pl.cur_slot[f] % store_frames) * g.L[0].px + (size_t)y0 * W;
-    const uint8_t* prv = store + (size_t)(pl.prev_slot[f] % store_frames) * g.L[0].px + (size_t)y0 * W;
+    const uint8_t* cur = store + (size_t)pl.cur_slot[f] * g.L[0].px + (size_t)y0 * W;
+    const uint8_t* prv = store + (size_t)pl.prev_slot[f] * g.L[0].px + (size_t)y0 * W;
     // ---- stage the two bands ----
     if (TMA) {                                   // W % 16 == 0: p0 == W, a band is rows * W contiguous, 16-byte aligned bytes
         if (tid == 0) {
