@@ -537,11 +537,6 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     c->lw[1] = 2 * (width / 3); c->lh[1] = 2 * (height / 3);
     for (int l = 2; l < N_LAYERS; l++) { c->lw[l] = c->lw[l - 2] / 2; c->lh[l] = c->lh[l - 2] / 2; }
     for (int l = 0; l < N_LAYERS; l++) { c->rows += c->lh[l]; c->pyr_px += c->lw[l] * c->lh[l]; }
-    if (score_tile_rows(c->lh) > score_tile_rows_max()) {      // cannot happen for heights <= 8192; refuse rather than truncate
-        fail(nullptr, MFK_ERR_ARG, "frame height %d needs more score-kernel tile rows than the launch table holds", height);
-        destroy(c);
-        return MFK_ERR_ARG;
-    }
     c->cand_cap_pair = cand_cap_pair > 0 ? cand_cap_pair : std::max(4096, c->pyr_px / 6);
     c->row_cap_pair = row_cap_pair > 0 ? row_cap_pair : std::max(1024, c->pyr_px / 48);
     const size_t F = (size_t)max_pairs;

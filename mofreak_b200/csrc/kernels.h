@@ -66,8 +66,6 @@ int launch_set_pairs(cudaStream_t, const int32_t* cur_host, const int32_t* prev_
 void launch_absdiff(cudaStream_t, const Geom&, const uint8_t* store, int store_frames, PairList, uint8_t* img);
 void launch_pyramid(cudaStream_t, const Geom&, uint8_t* img);                                  // layers 1..5
 int  score_mask_words(int frame_width);        // 64-bit hit-mask words per (pair, layer row)
-int  score_tile_rows(const int layer_heights[N_LAYERS]);   // tile rows of k_scores over all layers, and the table's capacity
-int  score_tile_rows_max();
 // k_scores' tensor maps of one lane's pyramid buffer (opaque here: CUtensorMap needs cuda.h), rebuilt when F or img change
 struct ScoreMapCache {
     int F = -1;

@@ -228,10 +228,10 @@ constexpr int SC_TW = 64, SC_TH = 32;                 // output tile
 constexpr int SC_SW = SC_TW + 8, SC_SH = SC_TH + 6;   // staged: columns x0-4 .. x0+67, rows y0-3 .. y0+34
 constexpr int SC_PW = SC_SW / 2;                      // 16-bit pixel pairs (words) per staged row
 
-struct ScoreTiles {                         // blockIdx.y = tile row over all layers -> its layer and first image row
-    int across[N_LAYERS];
-    uint8_t layer[768];                     // frames up to 8192 rows: 748 tile rows
-    int16_t y0[768];
+struct ScoreTiles {                         // blockIdx.x = tile of the pair, layers one after the other, row-major inside a layer
+    int across[N_LAYERS];                   // tile columns of each layer
+    int first[N_LAYERS + 1];                // first tile of each layer; [N_LAYERS] = tiles per pair
+    uint32_t magic[N_LAYERS];               // floor(2^32 / across) + 1 (0 for across = 1): tile / across by one multiply-high
 };
 
 // 8 pixels (two little-endian words w0, w1 and the byte after them) -> their four even-aligned and four odd-aligned
@@ -267,14 +267,17 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     __shared__ __align__(16) uint8_t score_tile[SC_TH][SC_TW];
     uint8_t* const raw = raw_or_queue;
     uint16_t* const hard = reinterpret_cast<uint16_t*>(raw_or_queue);
-    // grid = (widest layer's tile columns, tile rows of all layers, pairs): no division to find the tile; the blocks
-    // beyond a narrower layer's last column leave at once
-    const int f = blockIdx.z;
-    const int l = tiles.layer[blockIdx.y];
-    const int tcol = blockIdx.x;
-    if (tcol >= tiles.across[l]) return;
+    // grid = (tiles of a pair, pairs): exactly the live tiles (a grid of tile columns x tile rows of all layers launched 35 %
+    // of its blocks beyond the narrower layers' last column)
+    const int f = blockIdx.y;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < N_LAYERS; k++) l += ((int)blockIdx.x >= tiles.first[k]);
+    const int t = (int)blockIdx.x - tiles.first[l];
+    const int trow = tiles.magic[l] ? (int)__umulhi((uint32_t)t, tiles.magic[l]) : t;
+    const int tcol = t - trow * tiles.across[l];
     const LayerGeom& L = g.L[l];
-    const int x0 = tcol * SC_TW, y0 = tiles.y0[blockIdx.y];
+    const int x0 = tcol * SC_TW, y0 = trow * SC_TH;
     const int w = L.w, h = L.h;
     const uint8_t* img = img_all + L.base + (size_t)f * L.px;
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -434,9 +437,6 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
 }
 
 int score_mask_words(int frame_width) { return (frame_width + SC_TW - 1) / SC_TW; }
-int score_tile_rows(const int lh[N_LAYERS]) { int r = 0; for (int l = 0; l < N_LAYERS; l++) r += (lh[l] + SC_TH - 1) / SC_TH; return r; }
-int score_tile_rows_max() { return (int)(sizeof(ScoreTiles::layer) / sizeof(uint8_t)); }
-
 // cuTensorMapEncodeTiled through the runtime's driver entry-point lookup: the library does not link libcuda
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -482,15 +482,18 @@ static void refresh_score_maps(ScoreMapCache& cache, const Geom& g, const uint8_
 
 void launch_scores(cudaStream_t st, const Geom& g, const uint8_t* img, uint8_t* S, unsigned long long* hitmask, ScoreMapCache& cache) {
     ScoreTiles tiles;
-    int rows = 0, widest = 0;
+    int n = 0;
     for (int l = 0; l < N_LAYERS; l++) {
-        tiles.across[l] = (g.L[l].w + SC_TW - 1) / SC_TW;
-        widest = max(widest, tiles.across[l]);
-        for (int y = 0; y < g.L[l].h && rows < 768; y += SC_TH, rows++) { tiles.layer[rows] = (uint8_t)l; tiles.y0[rows] = (int16_t)y; }
+        const int across = (g.L[l].w + SC_TW - 1) / SC_TW, down = (g.L[l].h + SC_TH - 1) / SC_TH;
+        tiles.across[l] = across;
+        tiles.first[l] = n;
+        tiles.magic[l] = across <= 1 ? 0u : (uint32_t)(0x100000000ull / (uint32_t)across) + 1u;      // exact for tile * across < 2^32
+        n += across * down;
     }
+    tiles.first[N_LAYERS] = n;
     refresh_score_maps(cache, g, img);
-    // gridDim.z <= 65535 pairs per launch sequence (context.cu caps max_pairs far below)
-    k_scores<<<dim3(widest, rows, g.F), dim3(32, 8), 0, st>>>(g, tiles, *reinterpret_cast<const ScoreMaps*>(cache.blob), img, S, hitmask,
+    // gridDim.y <= 65535 pairs per launch sequence (context.cu caps max_pairs far below)
+    k_scores<<<dim3(n, g.F), dim3(32, 8), 0, st>>>(g, tiles, *reinterpret_cast<const ScoreMaps*>(cache.blob), img, S, hitmask,
                                                                score_mask_words(g.W));
 }
 

@@ -33,10 +33,18 @@ struct FrontLayout {                      // shared-memory plan of one band
     int off[N_LAYERS];                    // byte offsets: layer 0 = current frame (becomes the difference), then layers 1..5
     int off_prev;                         // previous frame's band
     int total;
+    uint32_t mg_items[N_LAYERS];          // div_magic of the work items per destination row (group) of each layer's sampler
+    uint32_t mg_words[N_LAYERS];          // div_magic of the words per row of each layer (copy_out)
 };
 
+// i / d for i < 65536, d <= 2048 by one multiply: m = floor(2^32 / d) + 1 is exact for i * d < 2^32 (0 stands for d = 1)
+// (computed on the host, FrontLayout: the 64-bit division costs a thread more than all the divisions it replaces)
+inline uint32_t div_magic(int d) { return d <= 1 ? 0u : (uint32_t)(0x100000000ull / (uint32_t)d) + 1u; }
+__device__ __forceinline__ int fast_div(int i, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)i, magic) : i; }
+
 // rows * w bytes from shared rows of pitch sp to global rows of pitch w (dense), widest stores the alignment allows
-__device__ __forceinline__ void copy_out(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int sp, int w, int rows, int tid) {
+__device__ __forceinline__ void copy_out(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int sp, int w, int rows, int tid,
+                                         const uint32_t mg) {
     if (rows <= 0) return;
     if (sp == w && (((uintptr_t)dst) & 15) == 0) {
         const uint4* s = reinterpret_cast<const uint4*>(src);
@@ -46,7 +54,7 @@ __device__ __forceinline__ void copy_out(uint8_t* __restrict__ dst, const uint8_
     } else if (((((uintptr_t)dst) | (uintptr_t)w) & 3) == 0) {
         const int words = w >> 2;
         for (int i = tid; i < rows * words; i += FR_THREADS) {
-            const int r = i / words, k = i - r * words;
+            const int r = fast_div(i, mg), k = i - r * words;
             reinterpret_cast<uint32_t*>(dst + (size_t)r * w)[k] = reinterpret_cast<const uint32_t*>(src + r * sp)[k];
         }
     } else {
@@ -61,13 +69,13 @@ __device__ __forceinline__ void copy_out(uint8_t* __restrict__ dst, const uint8_
 // shared rows of pitch dp.  Inside the paired 16-byte blocks four outputs come from two 8-byte reads per source row
 // (avg of avg, rounding up); the columns of an odd trailing block and of the leftover follow half_px's per-column rules.
 __device__ __forceinline__ void half_band(const uint8_t* __restrict__ src, int sp, int sw, uint8_t* __restrict__ dst, int dp, int dw,
-                                          int rows, int tid) {
+                                          int rows, int tid, const uint32_t mg) {
     if (rows <= 0) return;
     const int paired_out = ((sw >> 4) >> 1) * 16;
     const int quads = paired_out >> 2;
     const int items = quads + (dw - paired_out);
     for (int i = tid; i < rows * items; i += FR_THREADS) {
-        const int j = i / items, t = i - j * items;
+        const int j = fast_div(i, mg), t = i - j * items;
         if (t < quads) {
             const uint2 u = *reinterpret_cast<const uint2*>(src + (2 * j) * sp + 8 * t);
             const uint2 l = *reinterpret_cast<const uint2*>(src + (2 * j + 1) * sp + 8 * t);
@@ -115,13 +123,13 @@ __device__ __forceinline__ uint2 twothird_horizontal4(uint32_t L, uint32_t M, ui
 // code's own formulation, _mm_avg_epu8), byte permutes gather each triple's left / middle / right column; triples of the
 // trailing rule and a last incomplete quad take the per-triple form.
 __device__ __forceinline__ void twothird_band(const uint8_t* __restrict__ src, int sp, int sw, uint8_t* __restrict__ dst, int dp, int dw,
-                                              int groups, int tid) {
+                                              int groups, int tid, const uint32_t mg) {
     if (groups <= 0) return;
     const int triples = dw >> 1;
     const int in_blocks = 5 * (sw / 15);                   // triples that follow the block rule
     const int quads = (triples + 3) >> 2;
     for (int i = tid; i < groups * quads; i += FR_THREADS) {
-        const int gt = i / quads, q = i - gt * quads;
+        const int gt = fast_div(i, mg), q = i - gt * quads;
         const uint8_t* r1 = src + (3 * gt) * sp + 12 * q;
         uint8_t* d1 = dst + (2 * gt) * dp + 8 * q;
         if (4 * q + 4 <= in_blocks) {
@@ -136,7 +144,7 @@ __device__ __forceinline__ void twothird_band(const uint8_t* __restrict__ src, i
                 D[k] = __vavgu4(__vavgu4(cv, bv), cv);
             }
             // the triple whose index is 4 (mod 5) is the fifth of its 15-column block: its middle column is its left one
-            const int kk = (4 + q) % 5;
+            const int kk = (4 + q) - 5 * (int)__umulhi((uint32_t)(4 + q), 0x33333334u);      // (4 + q) % 5
             const uint32_t fifth = kk < 4 ? 0xffu << (8 * kk) : 0u;
             uint32_t L = __byte_perm(__byte_perm(U[0], U[1], 0x0630), U[2], 0x5210);
             uint32_t M = __byte_perm(__byte_perm(U[0], U[1], 0x0741), U[2], 0x6210);
@@ -207,7 +215,7 @@ k_front(const __grid_constant__ Geom g, const __grid_constant__ FrontLayout fl, 
     }
     __syncthreads();
     // ---- layer 0 out, its row strip sums, layers 1 and 2 into shared memory ----
-    copy_out(img_all + g.L[0].base + (size_t)f * g.L[0].px + (size_t)y0 * W, A, p0, W, rows, tid);
+    copy_out(img_all + g.L[0].base + (size_t)f * g.L[0].px + (size_t)y0 * W, A, p0, W, rows, tid, fl.mg_words[0]);
     {
         // sums of the 128-column strips of every row (a warp per (row, strip): one word per lane, one REDUX); the prefix over
         // the strips of a row - left[y][s], what k_integral_strips starts each row from - follows after the next barrier
@@ -229,24 +237,24 @@ k_front(const __grid_constant__ Geom g, const __grid_constant__ FrontLayout fl, 
     // rows of each layer this band produces (the layers' heights are not multiples of the band's share in general)
     const int n1 = min(8 * m, g.L[1].h - 8 * m * band), n2 = min(6 * m, g.L[2].h - 6 * m * band), n3 = min(4 * m, g.L[3].h - 4 * m * band);
     const int n4 = min(3 * m, g.L[4].h - 3 * m * band), n5 = min(2 * m, g.L[5].h - 2 * m * band);
-    twothird_band(A, p0, W, S1, fl.pitch[1], g.L[1].w, n1 > 0 ? n1 / 2 : 0, tid);
-    half_band(A, p0, W, S2, fl.pitch[2], g.L[2].w, n2, tid);
+    twothird_band(A, p0, W, S1, fl.pitch[1], g.L[1].w, n1 > 0 ? n1 / 2 : 0, tid, fl.mg_items[1]);
+    half_band(A, p0, W, S2, fl.pitch[2], g.L[2].w, n2, tid, fl.mg_items[2]);
     __syncthreads();
     if (tid < rows) {
         int32_t* out = left + ((size_t)f * H + y0 + tid) * strips;
         int carry = 0;
         for (int sidx = 0; sidx < strips; sidx++) { out[sidx] = carry; carry += strip_sum[tid * strips + sidx]; }
     }
-    copy_out(img_all + g.L[1].base + (size_t)f * g.L[1].px + (size_t)(8 * m * band) * g.L[1].w, S1, fl.pitch[1], g.L[1].w, n1, tid);
-    copy_out(img_all + g.L[2].base + (size_t)f * g.L[2].px + (size_t)(6 * m * band) * g.L[2].w, S2, fl.pitch[2], g.L[2].w, n2, tid);
-    half_band(S1, fl.pitch[1], g.L[1].w, S3, fl.pitch[3], g.L[3].w, n3, tid);
-    half_band(S2, fl.pitch[2], g.L[2].w, S4, fl.pitch[4], g.L[4].w, n4, tid);
+    copy_out(img_all + g.L[1].base + (size_t)f * g.L[1].px + (size_t)(8 * m * band) * g.L[1].w, S1, fl.pitch[1], g.L[1].w, n1, tid, fl.mg_words[1]);
+    copy_out(img_all + g.L[2].base + (size_t)f * g.L[2].px + (size_t)(6 * m * band) * g.L[2].w, S2, fl.pitch[2], g.L[2].w, n2, tid, fl.mg_words[2]);
+    half_band(S1, fl.pitch[1], g.L[1].w, S3, fl.pitch[3], g.L[3].w, n3, tid, fl.mg_items[3]);
+    half_band(S2, fl.pitch[2], g.L[2].w, S4, fl.pitch[4], g.L[4].w, n4, tid, fl.mg_items[4]);
     __syncthreads();
-    copy_out(img_all + g.L[3].base + (size_t)f * g.L[3].px + (size_t)(4 * m * band) * g.L[3].w, S3, fl.pitch[3], g.L[3].w, n3, tid);
-    copy_out(img_all + g.L[4].base + (size_t)f * g.L[4].px + (size_t)(3 * m * band) * g.L[4].w, S4, fl.pitch[4], g.L[4].w, n4, tid);
-    half_band(S3, fl.pitch[3], g.L[3].w, S5, fl.pitch[5], g.L[5].w, n5, tid);
+    copy_out(img_all + g.L[3].base + (size_t)f * g.L[3].px + (size_t)(4 * m * band) * g.L[3].w, S3, fl.pitch[3], g.L[3].w, n3, tid, fl.mg_words[3]);
+    copy_out(img_all + g.L[4].base + (size_t)f * g.L[4].px + (size_t)(3 * m * band) * g.L[4].w, S4, fl.pitch[4], g.L[4].w, n4, tid, fl.mg_words[4]);
+    half_band(S3, fl.pitch[3], g.L[3].w, S5, fl.pitch[5], g.L[5].w, n5, tid, fl.mg_items[5]);
     __syncthreads();
-    copy_out(img_all + g.L[5].base + (size_t)f * g.L[5].px + (size_t)(2 * m * band) * g.L[5].w, S5, fl.pitch[5], g.L[5].w, n5, tid);
+    copy_out(img_all + g.L[5].base + (size_t)f * g.L[5].px + (size_t)(2 * m * band) * g.L[5].w, S5, fl.pitch[5], g.L[5].w, n5, tid, fl.mg_words[5]);
 }
 
 }  // namespace
@@ -271,6 +279,13 @@ cudaError_t launch_front(cudaStream_t st, const Geom& g, const uint8_t* store, i
         if (l == 0) { fl.off_prev = at; at += band_rows[0] * mult * fl.pitch[0]; }
     }
     fl.total = at;
+    static const int SRC[N_LAYERS] = {-1, 0, 0, 1, 2, 3};          // brisk.cpp:578-587
+    for (int l = 0; l < N_LAYERS; l++) {
+        fl.mg_words[l] = div_magic(g.L[l].w >> 2);
+        if (l == 0) fl.mg_items[l] = 0;
+        else if (l == 1) fl.mg_items[l] = div_magic(((g.L[1].w >> 1) + 3) >> 2);                      // twothird_band: quads of column triples
+        else { const int paired_out = ((g.L[SRC[l]].w >> 4) >> 1) * 16; fl.mg_items[l] = div_magic((paired_out >> 2) + (g.L[l].w - paired_out)); }   // half_band: items
+    }
     const dim3 grid((g.H + FR_BAND * mult - 1) / (FR_BAND * mult), g.F);
     const bool tma = (g.W & 15) == 0;            // slots, bands and rows then start 16-byte aligned and a band is a multiple of 16 bytes
     cudaError_t e;
