@@ -348,54 +348,41 @@ k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tile
     }
     __syncthreads();
     // ---- step 1: a thread owns the centre pairs (x0 + 2 lane, +1) of rows y0 + ty + 8 jy; staged column of the pair's first
-    // pixel is 4 + 2 lane = word 2 + lane of E ----
+    // pixel is 4 + 2 lane = word 2 + lane of E.
+    // Each warp queues its own survivors (no block-wide scan or barrier) in (pixel slot, lane) order, so that queue neighbours are
+    // tile-row neighbours and the ring loads of step 2 stay nearly free of bank conflicts (lane-major order measured 57 M
+    // conflict wavefronts per launch instead of 32 M): one ballot per pixel slot, a survivor's place is the slot's base plus the
+    // survivors on lower lanes (POPC runs on the otherwise idle XU pipe; a byte-packed shuffle scan of all eight slots at once
+    // cost 120 instructions per warp, this 70).
     const int xa = x0 + 2 * lane;
     const bool in_lo = xa >= 3 && xa < w - 3, in_hi = xa + 1 >= 3 && xa + 1 < w - 3;
-    uint32_t mine = 0;                                  // bit 2 * jy + half: that pixel needs the full score
+    uint16_t* queue = hard + wrp * (SC_TW * SC_TH / 8);
+    const uint32_t below = (1u << lane) - 1u;
+    int nh = 0;
 #pragma unroll
     for (int jy = 0; jy < SC_TH / 8; jy++) {
         const int ly = wrp + 8 * jy;
         const int y = y0 + ly;
-        if (!(y >= 3 && y < h - 3) || !(in_lo || in_hi)) continue;
-        const uint32_t* e = &E[ly + 3][lane + 2];
-        const uint32_t* o = &O[ly + 3][lane + 2];
-        // ring in circle order (oast9_16.h:214-232); offset dx even -> E[k + dx/2], odd -> O[k + (dx-1)/2]
-        uint32_t r[16];
-        r[0] = o[-2];                 r[1] = o[-SC_PW - 2];         r[2] = e[-2 * SC_PW - 1];     r[3] = o[-3 * SC_PW - 1];
-        r[4] = e[-3 * SC_PW];         r[5] = o[-3 * SC_PW];         r[6] = e[-2 * SC_PW + 1];     r[7] = o[-SC_PW + 1];
-        r[8] = o[1];                  r[9] = o[SC_PW + 1];          r[10] = e[2 * SC_PW + 1];     r[11] = o[3 * SC_PW];
-        r[12] = e[3 * SC_PW];         r[13] = o[3 * SC_PW - 1];     r[14] = e[2 * SC_PW - 1];     r[15] = o[SC_PW - 2];
-        const uint32_t both = oast_bound_pair(r, e[0]);            // halves: bound + 256 of the two centres
-        if (in_lo && (both & 0xffffu) > 256u) mine |= 1u << (2 * jy);
-        if (in_hi && (both >> 16) > 256u) mine |= 1u << (2 * jy + 1);
-    }
-    // Each warp queues its own survivors (no block-wide scan or barrier) in (pixel slot, lane) order, so that queue
-    // neighbours are tile-row neighbours and the ring loads of step 2 stay nearly free of bank conflicts (lane-major order
-    // measured 57 M conflict wavefronts per launch instead of 32 M).  All eight slots are scanned AT ONCE: a thread's eight
-    // survivor bits are spread into the bytes of two words, one shuffle scan of the pair gives, per byte, how many lanes
-    // before this one survive in that slot; byte-wise prefix sums of the warp totals (a multiply) give each slot's base.
-    uint16_t* queue = hard + wrp * (SC_TW * SC_TH / 8);
-    int nh;
-    {
-        const uint32_t lo = ((mine & 0xfu) * 0x00204081u) & 0x01010101u;           // bit b -> byte b
-        const uint32_t hi = (((mine >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
-        uint32_t ilo = lo, ihi = hi;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t a = __shfl_up_sync(0xffffffffu, ilo, d), b = __shfl_up_sync(0xffffffffu, ihi, d);
-            if (lane >= d) { ilo += a; ihi += b; }                                  // counts <= 32: bytes never carry
+        if (!(y >= 3 && y < h - 3)) continue;                      // the same for the whole warp
+        uint32_t both = 0x01000100u;                               // halves: bound + 256 of the two centres
+        if (in_lo || in_hi) {
+            const uint32_t* e = &E[ly + 3][lane + 2];
+            const uint32_t* o = &O[ly + 3][lane + 2];
+            // ring in circle order (oast9_16.h:214-232); offset dx even -> E[k + dx/2], odd -> O[k + (dx-1)/2]
+            uint32_t r[16];
+            r[0] = o[-2];                 r[1] = o[-SC_PW - 2];         r[2] = e[-2 * SC_PW - 1];     r[3] = o[-3 * SC_PW - 1];
+            r[4] = e[-3 * SC_PW];         r[5] = o[-3 * SC_PW];         r[6] = e[-2 * SC_PW + 1];     r[7] = o[-SC_PW + 1];
+            r[8] = o[1];                  r[9] = o[SC_PW + 1];          r[10] = e[2 * SC_PW + 1];     r[11] = o[3 * SC_PW];
+            r[12] = e[3 * SC_PW];         r[13] = o[3 * SC_PW - 1];     r[14] = e[2 * SC_PW - 1];     r[15] = o[SC_PW - 2];
+            both = oast_bound_pair(r, e[0]);
         }
-        const uint32_t tlo = __shfl_sync(0xffffffffu, ilo, 31), thi = __shfl_sync(0xffffffffu, ihi, 31);
-        const uint32_t sum_lo = (tlo * 0x01010101u) >> 24;                          // survivors of slots 0..3 (<= 128)
-        nh = (int)(sum_lo + ((thi * 0x01010101u) >> 24));
-        // byte b: queue position of this thread's survivor in slot b = survivors of earlier slots + earlier lanes of this slot
-        const uint32_t plo = (ilo - lo) + tlo * 0x01010100u;
-        const uint32_t phi = (ihi - hi) + thi * 0x01010100u + sum_lo * 0x01010101u;   // <= 255 per byte
-        const uint32_t base = (uint32_t)((wrp << 6) | (2 * lane));                  // (tile row << 6) | tile column of pixel slot 0
-#pragma unroll
-        for (int b = 0; b < 8; b++)
-            if ((mine >> b) & 1u)
-                queue[((b < 4 ? plo : phi) >> (8 * (b & 3))) & 0xffu] = (uint16_t)(base + (((8 * (b >> 1)) << 6) | (b & 1)));
+        const bool s_lo = in_lo && (both & 0xffffu) > 256u, s_hi = in_hi && (both >> 16) > 256u;    // these pixels need the full score
+        const uint32_t b_lo = __ballot_sync(0xffffffffu, s_lo), b_hi = __ballot_sync(0xffffffffu, s_hi);
+        const uint32_t at = (uint32_t)((ly << 6) | (2 * lane));    // (tile row << 6) | tile column
+        if (s_lo) queue[nh + __popc(b_lo & below)] = (uint16_t)at;
+        nh += __popc(b_lo);
+        if (s_hi) queue[nh + __popc(b_hi & below)] = (uint16_t)(at + 1u);
+        nh += __popc(b_hi);
     }
     __syncwarp();
     // ---- step 2: full closed-form score of the queued pixels ----
