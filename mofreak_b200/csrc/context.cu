@@ -102,6 +102,7 @@ struct mfk_ctx {
     bool main_wait_pending = false;       // the next launch sequence orders its shared-row part after main_mark
     bool serial = false;
     bool prioritised = true;              // MFK_PRIORITY=0: one stream per lane (plus the integral side stream), no priorities
+    bool early_losers = true;             // MFK_EARLY_LOSERS=0: every detector hit becomes a candidate (k_scores drops none)
     bool tail_overlap = false;            // MFK_TAIL_OVERLAP=1: descriptor kernels of consecutive batches may overlap
     bool early_compact = true;            // MFK_EARLY_COMPACT=0: the whole second compaction waits for the previous tail
     bool fused_front = true;              // MFK_FUSED_FRONT=0 forces the separate dense kernels (A/B measurements, wide frames use them anyway)
@@ -336,7 +337,7 @@ int run_batch(mfk_ctx* c, const int32_t* cur, const int32_t* prev, const int32_t
         CU(c, cudaEventRecord(L.aux_join, L.aux_stream));
     }
     if (!fused) { Span s(c, P_PYRAMID, 5, ds);   launch_pyramid(ds, g, L.maps.img); }
-    { Span s(c, P_SCORES, 1, ds);    launch_scores(ds, g, L.maps.img, L.maps.S, L.hitmask, L.score_maps); }
+    { Span s(c, P_SCORES, 1, ds);    launch_scores(ds, g, L.maps.img, L.maps.S, c->early_losers ? L.maps.status : nullptr, L.hitmask, L.score_maps); }
     if (ds != st) { CU(c, cudaEventRecord(L.scored, ds)); CU(c, cudaStreamWaitEvent(st, L.scored, 0)); }
     { Span s(c, P_SCAN, 4, st);      launch_row_counts(st, g, L.hitmask, L.cb.row_count);
                                      launch_exclusive_scan(st, L.cb.row_count, F * g.rows, nullptr, L.scan_scratch); }
@@ -508,6 +509,7 @@ int mfk_create_ex(mfk_ctx** out, int device, int width, int height, int store_fr
     if (const char* e = getenv("MFK_PRIORITY")) c->prioritised = atoi(e) != 0;
     if (const char* e = getenv("MFK_EARLY_COMPACT")) c->early_compact = atoi(e) != 0;
     if (const char* e = getenv("MFK_TAIL_OVERLAP")) c->tail_overlap = atoi(e) != 0;
+    if (const char* e = getenv("MFK_EARLY_LOSERS")) c->early_losers = atoi(e) != 0;
     int prio_low = 0, prio_high = 0;
     CUC(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
     for (int li = 0; li < c->lanes_built; li++) {

@@ -72,7 +72,7 @@ struct ScoreMapCache {
     const uint8_t* img = nullptr;
     alignas(64) unsigned char blob[N_LAYERS * 128 + 64];
 };
-void launch_scores(cudaStream_t, const Geom&, const uint8_t* img, uint8_t* S, unsigned long long* hitmask, ScoreMapCache& cache);
+void launch_scores(cudaStream_t, const Geom&, const uint8_t* img, uint8_t* S, uint8_t* status_or_null, unsigned long long* hitmask, ScoreMapCache& cache);
 void launch_row_counts(cudaStream_t, const Geom&, const unsigned long long* hitmask, uint32_t* row_count);
 void launch_fill_candidates(cudaStream_t, const Geom&, const unsigned long long* hitmask, CandBuf);
 // left_done: the per-row strip sums were already written by launch_front
