@@ -583,8 +583,8 @@ def run_ours(args, name, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="trecvid", choices=sorted(CONFIGS), help="BASELINE configuration (headline: trecvid)")
     ap.add_argument("--videos", type=int, default=0, help="videos (streams / clips) per GPU per step; 0 = the configuration's")

@@ -35,7 +35,8 @@ def main():
         short = k.replace("mfk::", "").replace("(anonymous namespace)::", "")
         print("| `%s` | %d | " % (short, sum(c.values())) + " | ".join(str(c.get(m, 0)) for m in MARK) +
               " | " + ", ".join("%s %d" % kv for kv in c.most_common(6)) + " |")
-    print("\nTMA evidence: `UBLKCP.S.G` (cp.async.bulk global->shared) appears in `k_front<true>` (two frame bands per block) and "
+    print("\nTMA evidence: `UTMALDG.2D` (cp.async.bulk.tensor.2d, one 38 x 96-byte box per tile from a tensor map in the kernel "
+          "parameters) in `k_scores`; `UBLKCP.S.G` (cp.async.bulk global->shared) in `k_front<true>` (two frame bands per block) and "
           "`k_bow_assign` (the codebook); their completion is awaited on mbarriers (`SYNCS.ARRIVE.TRANS64` / `SYNCS.PHASECHK`). "
           "No kernel uses tensor cores (no UTC*MMA / HMMA): no stage of the path is a dense contraction.")
     excerpt = [l for l in sass.splitlines() if re.search(r"UBLKCP|SYNCS\.|VIMNMX3|REDUX", l)]
