@@ -2,6 +2,10 @@
 seeded inputs and with the committed golden fixtures; full-size cases use size-independent properties.
 Bar: bit-exact — keypoint coordinates are float32 but must be IDENTICAL (tolerance 0), as are all descriptor
 bytes and bag-of-words indices."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -502,3 +506,45 @@ def test_host_buffers_from_the_library(wc):
         got, _ = ctx.fetch_rows(len(want) + 8)
         assert util.rows_equal(got, want) and len(want) > 0
     buf.close()
+
+
+_SWITCH_CACHE = {}
+_SWITCH_SCRIPT = r"""
+import hashlib, sys
+sys.path.insert(0, %r)
+import mofreak_b200
+out = []
+for (w, h, n, seed) in [(720, 576, 7, 13), (367, 251, 8, 15), (160, 120, 14, 11)]:
+    clip = mofreak_b200.synth_clip(w, h, n, seed)
+    with mofreak_b200.Context(w, h, max(16, n), 3) as ctx:
+        rows = ctx.extract_clip(clip)
+    out.append("%%d:%%s" %% (len(rows), hashlib.sha256(rows.tobytes()).hexdigest()))
+print(" ".join(out))
+"""
+
+
+@pytest.mark.parametrize("env", [{"MFK_SCORES_NO_TENSOR_MAP": "1"}, {"MFK_EARLY_LOSERS": "0"}, {"MFK_PRIORITY": "0", "MFK_EARLY_COMPACT": "0"},
+                                 {"MFK_TAIL_OVERLAP": "1", "MFK_LANES": "2"}, {"MFK_FUSED_FRONT": "0", "MFK_PB_GROUP": "256"}])
+def test_measurement_switches_do_not_change_the_rows(env):
+    """The environment switches choose between implementations of the same step (tile staging by the TMA tensor copy or by
+    thread loads, early removal of 8-neighbour losers, stream priorities, lane count, fused or separate dense front, phase B
+    group size): whatever they are set to, the rows are the same bytes.  Each setting runs in a process of its own because the
+    library reads the switches once."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = _SWITCH_SCRIPT % root
+
+    def run(extra):
+        e = dict(os.environ)
+        for k in ("MFK_SCORES_NO_TENSOR_MAP", "MFK_EARLY_LOSERS", "MFK_PRIORITY", "MFK_EARLY_COMPACT", "MFK_TAIL_OVERLAP", "MFK_LANES",
+                  "MFK_FUSED_FRONT", "MFK_PB_GROUP", "MFK_PA_BLOCKS", "MFK_DESC_BLOCKS"):
+            e.pop(k, None)
+        e.update(extra)
+        r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600, env=e)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return r.stdout.strip().splitlines()[-1]
+
+    if "base" not in _SWITCH_CACHE:
+        _SWITCH_CACHE["base"] = run({})
+    base = _SWITCH_CACHE["base"]
+    assert base.count(":") == 3 and not base.startswith("0:")
+    assert run(env) == base
