@@ -388,25 +388,36 @@ def run_ours(args, name, cfg):
         # and kernels of the other.  Every stream is a frame RING of 2 x SEGS segments of P slots on the device: a turn writes
         # the stream's new frames into the segments the previous turn did not use; the 5 frames of look-back are still
         # there - nothing is uploaded twice.
-        groups = [list(range(0, V // 2)), list(range(V // 2, V))] if V >= 2 and V % 2 == 0 else [list(range(V))]
-        SEGS = len(groups)                  # segments of P frames a turn appends to each stream of its group
+        n_groups = 2 if V >= 2 and V % 2 == 0 else 1
+        SEGS = n_groups                     # segments of P frames a turn appends to each stream of its group
         ring = 2 * SEGS * P
         chunk_v = max(1, MAX_PAIRS // P)
         e2e_ctx = []
-        for vids in groups:
-            c = mofreak_b200.Context(W, H, len(vids) * ring, MAX_PAIRS, device=local_rank)
-            rows_host = torch.empty((row_cap, 32), dtype=torch.uint8, pin_memory=True)
-            # initial look-back f0..f4 at the end of the ring (what the first forward segment looks back to)
-            for j, v in enumerate(vids):
-                c.upload_raw(host.ptr + v * HPV * frame_bytes, GAP, j * ring + ring - GAP)
-            c.sync()
-            # chunks of whole streams: a short first chunk, so that the first kernels start early
-            sizes, left = [], len(vids)
-            if len(vids) > chunk_v >= 2:
-                sizes += [1, chunk_v - 1]; left -= chunk_v
-            while left > 0:
-                sizes.append(min(chunk_v, left)); left -= sizes[-1]
-            e2e_ctx.append({"ctx": c, "rows": rows_host, "vids": vids, "sizes": sizes, "seg": 0})
+
+        def build_stream_contexts(per_group):
+            """Two contexts (groups) of `per_group` streams each; a stream's frames come from host stream (index % V)."""
+            for e in e2e_ctx:
+                e["ctx"].close()
+            del e2e_ctx[:]
+            cap = int(n_rows_step * 1.5 * max(1.0, per_group * n_groups / V)) + 65536
+            for g in range(n_groups):
+                vids = [(g * per_group + j) % V for j in range(per_group)]
+                c = mofreak_b200.Context(W, H, len(vids) * ring, MAX_PAIRS, device=local_rank)
+                rows_host = torch.empty((cap, 32), dtype=torch.uint8, pin_memory=True)
+                # initial look-back f0..f4 at the end of the ring (what the first forward segment looks back to)
+                for j, v in enumerate(vids):
+                    c.upload_raw(host.ptr + v * HPV * frame_bytes, GAP, j * ring + ring - GAP)
+                c.sync()
+                # chunks of whole streams: a short first chunk, so that the first kernels start early
+                sizes, left = [], len(vids)
+                if len(vids) > chunk_v >= 2:
+                    sizes += [1, chunk_v - 1]; left -= chunk_v
+                while left > 0:
+                    sizes.append(min(chunk_v, left)); left -= sizes[-1]
+                e2e_ctx.append({"ctx": c, "rows": rows_host, "vids": vids, "sizes": sizes, "seg": 0, "cap": cap})
+
+        per_group = V // n_groups
+        build_stream_contexts(per_group)
         i_in = np.arange(P)
 
         def submit(e):
@@ -434,7 +445,6 @@ def run_ours(args, name, cfg):
                 e["seg"] = k + 1
             for cu, pr, lb in todo:
                 c.extract_pairs(cu, pr, lb)
-        h2d_per_step = V * P * frame_bytes
     else:
         # clips: whole steps alternate between two contexts; a step uploads every frame of every clip
         chunk_v = max(1, MAX_PAIRS // P)
@@ -442,7 +452,7 @@ def run_ours(args, name, cfg):
         for _ in range(2):
             c = mofreak_b200.Context(W, H, n_frames, MAX_PAIRS, device=local_rank)
             c.bow_set_codebook(codebook)
-            e2e_ctx.append({"ctx": c, "rows": torch.empty((row_cap, 32), dtype=torch.uint8, pin_memory=True)})
+            e2e_ctx.append({"ctx": c, "rows": torch.empty((row_cap, 32), dtype=torch.uint8, pin_memory=True), "cap": row_cap})
 
         def submit(e):
             c = e["ctx"]
@@ -459,12 +469,11 @@ def run_ours(args, name, cfg):
                 v1 = min(V, v0 + chunk_v)
                 ps = slice(v0 * P, v1 * P)
                 c.extract_pairs(cur[ps], prev[ps], label[ps])
-        h2d_per_step = n_frames * frame_bytes
 
     def collect(e):
         if cfg["bow"]:
             e["ctx"].bow_histogram_videos(ppv)       # configs[2]: per-clip word counts belong to the step (blocks; the other context works)
-        return e["ctx"].fetch_rows_raw(e["rows"].data_ptr(), row_cap)
+        return e["ctx"].fetch_rows_raw(e["rows"].data_ptr(), e["cap"])
 
     def run_e2e(steps):
         """Returns the average number of rows fetched per step."""
@@ -480,6 +489,42 @@ def run_ours(args, name, cfg):
         return acc / max(1, steps)
 
     run_e2e(max(2, args.warmup))
+    # ---- N > 1, streams: the host->device links of one box do not carry the same rate when all of them are busy (eight ranks:
+    # 23 GB/s on the slowest, 30 GB/s on average, profiles/h2d_ceiling.json), and end to end every rank is bound by its link.  So
+    # streams are assigned to the GPUs in proportion to the rate each rank sustains while ALL ranks run (measured here over a
+    # fixed wall time), keeping the box's total: a rank then advances `per_group` streams per step instead of V / 2. ----
+    balance = None
+    if world > 1 and streams_mode and not args.no_balance:
+        barrier()
+        t_cal, n_cal = time.perf_counter(), 0
+        while n_cal < 4 or time.perf_counter() - t_cal < 0.6:
+            run_e2e(2)
+            n_cal += 2
+        for e in e2e_ctx:
+            e["ctx"].sync()
+        rate = n_cal / (time.perf_counter() - t_cal)
+        rates = torch.zeros(world, dtype=torch.float64, device="cuda")
+        rates[rank] = rate
+        dist.all_reduce(rates)
+        rates = rates.cpu().numpy()
+        total = per_group * world                            # streams per group over the box stay what they were
+        share = rates / rates.sum() * total
+        assign = np.clip(np.floor(share).astype(int), 2, 2 * per_group)
+        order = np.argsort(-(share - np.floor(share)), kind="stable")      # largest remainders take what is left (the same on every rank)
+        i = 0
+        while assign.sum() < total and i < 4 * world:
+            r = order[i % world]
+            if assign[r] < 2 * per_group:
+                assign[r] += 1
+            i += 1
+        balance = {"steps_per_s_per_rank_equal_shares": [float(x) for x in rates], "streams_per_group_per_rank": [int(x) for x in assign]}
+        if int(assign[rank]) != per_group:
+            per_group = int(assign[rank])
+            build_stream_contexts(per_group)
+        barrier()
+        run_e2e(2)
+    frames_per_step_e2e = (per_group * n_groups * P) if streams_mode else n_pairs
+    h2d_per_step = (frames_per_step_e2e if streams_mode else n_frames) * frame_bytes
     launches_e2e0 = sum(e["ctx"].launch_count() for e in e2e_ctx)
     barrier()
     t0 = time.perf_counter()
@@ -497,16 +542,16 @@ def run_ours(args, name, cfg):
         t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_res, ms_e2e = float(t[0]), float(t[1])
-        r = torch.tensor([float(n_rows_step)], dtype=torch.float64, device="cuda")
+        r = torch.tensor([float(n_rows_step), float(frames_per_step_e2e), float(h2d_per_step)], dtype=torch.float64, device="cuda")
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
-        rows_all = float(r[0])
+        rows_all, frames_step_e2e_all, h2d_per_step = float(r[0]), float(r[1]), float(r[2]) / world      # bytes: mean over the ranks
     else:
-        rows_all = float(n_rows_step)
+        rows_all, frames_step_e2e_all = float(n_rows_step), float(frames_per_step_e2e)
 
     if rank == 0:
         frames_all = world * n_pairs * args.steps
         value = frames_all / (ms_res / 1e3)
-        e2e = frames_all / (ms_e2e / 1e3)
+        e2e = frames_step_e2e_all * args.steps / (ms_e2e / 1e3)
         rows_per_frame = n_rows_step / n_pairs
         # dominant kernel family by device time inside the timed region
         fam = {k: v for k, v in prof.items() if v[0] > 0 and k not in ("mip_only", "text") and (cfg["bow"] or k != "bow_assign")}
@@ -533,12 +578,16 @@ def run_ours(args, name, cfg):
             "rows_per_frame": rows_per_frame,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(rows_e2e) * 32,
                     "ms_per_step": ms_e2e / args.steps, "gpu_launches": int(launches_e2e), "contexts": 2,
+                    "link_balance": balance,
                     "h2d_gb_per_s_per_gpu": h2d_per_step / (ms_e2e / args.steps * 1e-3) / 1e9,
                     "h2d_ceiling_gb_per_s_per_gpu": ((ceiling or {}).get(str(world)) or {}).get("gb_per_s_per_gpu_min"),
                     "h2d_ceiling_source": "profiles/h2d_ceiling.json (copies only, same buffers and chunk sizes, %d ranks)" % world if ceiling else None,
                     "frames": ("continuous streams in two groups of %d, one group per context: a step advances one group by %d new frames per "
                                "stream (= %d processed frames), written into device frame rings; the 5-frame look-back stays resident, "
-                               "nothing is uploaded twice" % (V // 2, 2 * P, V * P)) if streams_mode else "clips: every step uploads every frame of every clip",
+                               "nothing is uploaded twice" % (V // 2, 2 * P, V * P) +
+                               ("; with N > 1 the streams of the box are assigned to the ranks in proportion to the host->device rate each rank "
+                                "sustains while all ranks run (link_balance): a rank's step advances streams_per_group_per_rank streams" if balance else ""))
+                              if streams_mode else "clips: every step uploads every frame of every clip",
                     "timing": "host clock around the K steps, device synchronised on both sides (every fetch blocks, so "
                               "this bounds the device time from above); two contexts take turns so that the row fetch of one "
                               "overlaps the uploads and kernels of the other"},
@@ -590,6 +639,7 @@ def main():
     ap.add_argument("--videos", type=int, default=0, help="videos (streams / clips) per GPU per step; 0 = the configuration's")
     ap.add_argument("--max-pairs", type=int, default=0, help="frame pairs per internal launch sequence; 0 = the configuration's")
     ap.add_argument("--distinct", type=int, default=0, help="generate only this many distinct clips and repeat them (large clip sets)")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: every rank takes the same number of streams end to end (no link-rate balancing)")
     ap.add_argument("--wc", type=int, default=0, help="1: write-combined page-locked frame buffer for the end-to-end leg")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
