@@ -22,15 +22,16 @@ __device__ __forceinline__ int float_bits(float f) {
 // sequence with IEEE float ops gives the identical bit pattern for every input (checked against libm for
 // every integer pair in [-700, 700]^2 and random pairs by tests/test_device_source_cpu.py through the CPU harness).
 __device__ __forceinline__ float atanf_fdlibm(float x) {
-    const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
-    const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    // atan(0.5), atan(1), atan(1.5), atan(inf): high and low parts, picked by selects (an indexed array would live in local memory)
+    const float hi0 = 4.6364760399e-01f, hi1 = 7.8539812565e-01f, hi2 = 9.8279368877e-01f, hi3 = 1.5707962513e+00f;
+    const float lo0 = 5.0121582440e-09f, lo1 = 3.7748947079e-08f, lo2 = 3.4473217170e-08f, lo3 = 7.5497894159e-08f;
     const float aT[11] = {3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f,
                           9.0908870101e-02f, -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f,
                           4.9768779427e-02f, -3.6531571299e-02f, 1.6285819933e-02f};
     const int hx = float_bits(x);
     const int ix = hx & 0x7fffffff;
     int id;
-    if (ix >= 0x4c800000) return hx > 0 ? atanhi[3] + atanlo[3] : -atanhi[3] - atanlo[3];
+    if (ix >= 0x4c800000) return hx > 0 ? hi3 + lo3 : -hi3 - lo3;
     if (ix < 0x3ee00000) {
         if (ix < 0x31000000) return x;
         id = -1;
@@ -49,7 +50,9 @@ __device__ __forceinline__ float atanf_fdlibm(float x) {
     const float s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
     const float s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
     if (id < 0) return x - x * (s1 + s2);
-    const float r = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+    const float ahi = id == 0 ? hi0 : (id == 1 ? hi1 : (id == 2 ? hi2 : hi3));
+    const float alo = id == 0 ? lo0 : (id == 1 ? lo1 : (id == 2 ? lo2 : lo3));
+    const float r = ahi - ((x * (s1 + s2) - alo) - x);
     return hx < 0 ? -r : r;
 }
 
@@ -202,10 +205,23 @@ __device__ __forceinline__ int mip_ssd(const uint8_t* cur19, const uint8_t* prev
     const int sx = (int)((0x14787410u >> (4 * k)) & 15u) - 4, sy = (int)((0x10147874u >> (4 * k)) & 15u) - 4;
     const uint8_t* p = cur19 + (cy - 1) * PATCH + (cx - 1);
     const uint8_t* q = prev19 + (cy + sy - 1) * PATCH + (cx + sx - 1);
+#ifdef __CUDA_ARCH__
+    // 9 bytes from any byte offset = three aligned words and two funnel shifts per patch (the buffers are word aligned and padded);
+    // |p - q| per byte (VABSDIFF4), then the dot product of the differences with themselves (dp4a): exact, 19 instead of 36 instructions
+    const uint32_t pa = (uint32_t)(uintptr_t)p, qa = (uint32_t)(uintptr_t)q;
+    const uint32_t* pw = reinterpret_cast<const uint32_t*>(p - (pa & 3u));
+    const uint32_t* qw = reinterpret_cast<const uint32_t*>(q - (qa & 3u));
+    const uint32_t ps = (pa & 3u) * 8u, qs = (qa & 3u) * 8u;
+    const uint32_t p0 = pw[0], p1 = pw[1], p2 = pw[2], q0 = qw[0], q1 = qw[1], q2 = qw[2];
+    const uint32_t d0 = __vabsdiffu4(__funnelshift_r(p0, p1, ps), __funnelshift_r(q0, q1, qs));
+    const uint32_t d1 = __vabsdiffu4(__funnelshift_r(p1, p2, ps), __funnelshift_r(q1, q2, qs));
+    const uint32_t d2 = __vabsdiffu4((p2 >> ps) & 0xffu, (q2 >> qs) & 0xffu);
+    return (int)__dp4a(d2, d2, __dp4a(d1, d1, __dp4a(d0, d0, 0u)));
+#else
     int ssd = 0;
-#pragma unroll
     for (int i = 0; i < 9; i++) { const int d = (int)p[i] - (int)q[i]; ssd += d * d; }
     return ssd;
+#endif
 }
 
 // FREAK orientation bin from the two weighted gradient sums (cv::FREAK::computeImpl): the angle in degrees is

@@ -33,7 +33,7 @@ struct WarpScratch {
     alignas(16) uint8_t roi[2][ROI_MAX * ROI_STRIDE];
     alignas(16) RowTap rtap[PATCH];   // per destination row / column of the 19 x 19 patch
     alignas(16) ColTap ctap[PATCH];
-    uint8_t cur[PATCH_PAD], prev[PATCH_PAD];
+    alignas(4) uint8_t cur[PATCH_PAD], prev[PATCH_PAD];     // word aligned and padded: mip_ssd reads them as aligned words
     uint8_t field[2][44];             // receptive-field means: unrotated, rotated
 };
 
@@ -144,7 +144,7 @@ __device__ __forceinline__ void mip_bits(const WarpScratch& ws, int lane, uint32
 
 }  // namespace
 
-__global__ void __launch_bounds__(DW * 32)          // (forcing 6 blocks per SM at 40 registers measured 6 % slower than 5 at 48, twice)
+__global__ void __launch_bounds__(DW * 32, 5)       // 5 blocks per SM at 48 registers (forcing 6 at 40 measured 6 % slower, twice)
 k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ store, int store_frames, PairList pl,
            const int32_t* __restrict__ integral, CandBuf cb, DeviceTables tb, RowOut* __restrict__ rows) {
     __shared__ WarpScratch scratch[DW];
