@@ -211,8 +211,9 @@ void launch_pyramid(cudaStream_t st, const Geom& g, uint8_t* img) {
 // S_full(p) = clamp(max over the 16 arcs of 9 contiguous ring pixels of min(v_i - p) resp. min(p - v_i), minus
 // 1, to [0, 254]) — the value cornerScore's bisection converges to from b0 = 0 (oast9_16_nms.cc:42-2115), and
 // detect() at threshold b fires exactly where S_full >= b (oast9_16.cc:46).
-// One launch covers all six layers of all pairs: grid = (tile column, tile row over all layers, pair) of 64x32 tiles; a
-// block of 256 threads stages the tile plus its 3-px halo and scores it in two steps:
+// One launch covers all six layers of all pairs: grid = (tile of the pair over all layers, pair) of 64x32 tiles; a block of
+// 256 threads stages the tile plus its 3-px halo (one TMA tensor copy where the layer's rows are 16-byte aligned, see the
+// kernel) and scores it in two steps:
 //   1. every pixel: the antipodal-pair BOUND  S <= max(min_j max(v_j, v_j+8) - p, p - max_j min(v_j, v_j+8)) - 1  (an arc of 9
 //      contains one pixel of each antipodal pair).  bound <= 0 proves S = 0: most pixels of a difference image.  This
 //      step runs on PAIRS of horizontally adjacent centres packed into the two 16-bit halves of a word
@@ -222,8 +223,8 @@ void launch_pyramid(cudaStream_t st, const Geom& g, uint8_t* img) {
 //   2. the survivors (~20 % on noisy difference images), queued per warp so that full warps score them: 17 16-bit loads,
 //      each widened to (v, 255 - v) in the halves of a word, so that ONE 3-input packed minimum (VIMNMX3.U16x2) serves the
 //      brighter and the darker test at once: 16 + 16 packed min3 build the 16 arc minima, 8 packed max3 reduce them.
-// Scores land in a shared 64x32 byte tile that leaves with 32-bit stores (zeros included: no clearing of S); hits
-// (S >= 30) leave as one 64-bit mask per tile row.
+// Scores land in a shared 64x32 byte tile that leaves with 64-bit stores (zeros included: no clearing of S); hits
+// (S >= 30) that do not lose the 8-neighbour test inside the tile leave as one 64-bit mask per tile row.
 constexpr int SC_TW = 64, SC_TH = 32;                 // output tile
 constexpr int SC_SW = SC_TW + 8, SC_SH = SC_TH + 6;   // staged: columns x0-4 .. x0+67, rows y0-3 .. y0+34
 constexpr int SC_PW = SC_SW / 2;                      // 16-bit pixel pairs (words) per staged row
@@ -255,7 +256,7 @@ struct ScoreMaps {                          // one 2-D tensor map per layer whos
 };
 static_assert(sizeof(ScoreMaps) == sizeof(ScoreMapCache::blob), "ScoreMapCache::blob holds a ScoreMaps");
 
-__global__ void __launch_bounds__(256, 8)          // 8 blocks per SM: 32 registers, 21 KB of shared memory each
+__global__ void __launch_bounds__(256, 8)          // 8 blocks per SM: 32 registers, 18 KB of shared memory each
 k_scores(const __grid_constant__ Geom g, const __grid_constant__ ScoreTiles tiles, const __grid_constant__ ScoreMaps tmaps,
          const uint8_t* __restrict__ img_all, uint8_t* __restrict__ S_all, uint8_t* __restrict__ status_all,
          unsigned long long* __restrict__ hitmask, int mask_words) {
