@@ -246,6 +246,7 @@ def run_ours(args, name, cfg):
     import torch
     import torch.distributed as dist
     import mofreak_b200
+    from mofreak_b200 import sharding
 
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
@@ -507,16 +508,7 @@ def run_ours(args, name, cfg):
         rates[rank] = rate
         dist.all_reduce(rates)
         rates = rates.cpu().numpy()
-        total = per_group * world                            # streams per group over the box stay what they were
-        share = rates / rates.sum() * total
-        assign = np.clip(np.floor(share).astype(int), 2, 2 * per_group)
-        order = np.argsort(-(share - np.floor(share)), kind="stable")      # largest remainders take what is left (the same on every rank)
-        i = 0
-        while assign.sum() < total and i < 4 * world:
-            r = order[i % world]
-            if assign[r] < 2 * per_group:
-                assign[r] += 1
-            i += 1
+        assign = sharding.balance_streams(rates, per_group)      # streams per group over the box stay what they were
         balance = {"steps_per_s_per_rank_equal_shares": [float(x) for x in rates], "streams_per_group_per_rank": [int(x) for x in assign]}
         if int(assign[rank]) != per_group:
             per_group = int(assign[rank])

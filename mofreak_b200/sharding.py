@@ -38,6 +38,28 @@ def shard_stream(n_frames, world):
     return out
 
 
+def balance_streams(rates, streams_per_rank, lo=2):
+    """Streams for each rank in proportion to the rate it sustains (end to end every rank is bound by its host->device link,
+    and the links of one box do not carry the same rate when all of them are busy: eight B200s, 18 GB/s on four of them and
+    29.5 GB/s on the other four).  The box's total `streams_per_rank * len(rates)` is kept; a rank gets between `lo` and
+    twice `streams_per_rank`; largest remainders take what flooring leaves (ties by rank), so every rank that holds the same
+    `rates` computes the same assignment."""
+    rates = [max(0.0, float(r)) for r in rates]
+    world, total, hi = len(rates), streams_per_rank * len(rates), 2 * streams_per_rank
+    if world == 0 or sum(rates) <= 0.0:
+        return [streams_per_rank] * world
+    share = [r / sum(rates) * total for r in rates]
+    out = [min(hi, max(lo, int(x))) for x in share]
+    order = sorted(range(world), key=lambda k: (-(share[k] - int(share[k])), k))
+    i = 0
+    while sum(out) < total and i < 4 * world:
+        k = order[i % world]
+        if out[k] < hi:
+            out[k] += 1
+        i += 1
+    return out
+
+
 def allreduce_counts(counts, group=None):
     """Sums integer word counts over the ranks of a torch.distributed group (NCCL on GPU tensors, gloo on CPU
     tensors); in place, returns the tensor."""

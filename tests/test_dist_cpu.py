@@ -25,6 +25,26 @@ def test_shard_stream_covers_every_processed_frame_once():
                 assert first == a - 5 and first >= 0
 
 
+def test_balance_streams_keeps_the_total_and_follows_the_rates():
+    # the measured case: eight ranks, four links at 42.4 and four at 69.5 steps/s, 8 streams per group and rank
+    rates = [42.38, 42.76, 42.66, 42.40, 69.96, 69.04, 68.81, 69.47]
+    assert sharding.balance_streams(rates, 8) == [6, 6, 6, 6, 10, 10, 10, 10]
+    assert sharding.balance_streams([97.8, 93.9], 8) == [8, 8]                 # equal links: nothing changes
+    assert sharding.balance_streams([1.0], 8) == [8]
+    assert sharding.balance_streams([0.0, 0.0], 8) == [8, 8]                   # no measurement: equal shares
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        world = int(rng.integers(1, 9))
+        per = int(rng.integers(1, 17))
+        rates = rng.uniform(0.2, 3.0, world)
+        got = sharding.balance_streams(rates, per)
+        assert len(got) == world and all(min(2, per) <= g <= 2 * per for g in got)
+        if all(per * world * r / rates.sum() >= 2 for r in rates) and all(per * world * r / rates.sum() <= 2 * per - 1 for r in rates):
+            assert sum(got) == per * world                                     # nobody was clamped: the total is kept
+            assert all(abs(g - per * world * r / rates.sum()) < 1.0 + 1e-9 for g, r in zip(got, rates))
+        assert got == sharding.balance_streams(list(rates), per)               # deterministic
+
+
 def test_shard_clips_balances_and_partitions():
     lengths = [400, 100, 250, 399, 20, 5, 3, 120]
     for world in (1, 2, 4, 8):
