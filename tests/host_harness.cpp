@@ -71,6 +71,10 @@ struct Harness {
         tb.orient = T.orient; tb.used = T.used; tb.mip_needed = T.mip_needed; tb.n_mip_needed = T.n_mip_needed;
     }
 
+    // prune_tile_losers: what k_scores does with MFK_EARLY_LOSERS (the default): a hit with a strictly larger score among its 8
+    // neighbours that lies inside the 1-pixel frame of its 64 x 32 score tile gets status 0 and never becomes a candidate
+    bool prune_tile_losers = false;
+
     void dense(const uint8_t* diff) {
         memcpy(img.data(), diff, g.L[0].px);
         static const int SRC[6] = {-1, 0, 0, 1, 2, 3};
@@ -112,7 +116,24 @@ struct Harness {
                         }
                     }
                     S[L.base + y * L.w + x] = (uint8_t)s;
-                    if (s >= BRISK_THRESHOLD) { xy.push_back((uint32_t)x | ((uint32_t)y << 16)); meta.push_back((uint32_t)l); row_count[L.row0 + y]++; }
+                }
+            // the candidate list of the layer, in raster order (scores of the whole layer are known now, as in the kernel's tile)
+            const uint8_t* Sl = S.data() + L.base;
+            for (int y = 0; y < L.h; y++)
+                for (int x = 0; x < L.w; x++) {
+                    const int s = Sl[y * L.w + x];
+                    if (s < BRISK_THRESHOLD) continue;
+                    if (prune_tile_losers) {
+                        const int lx = x % 64, ly = y % 32;                 // SC_TW x SC_TH tiles start at multiples of 64 / 32
+                        if (lx >= 1 && lx <= 62 && ly >= 1 && ly <= 30) {
+                            int mx = 0;
+                            for (int dy = -1; dy <= 1; dy++)
+                                for (int dx = -1; dx <= 1; dx++)
+                                    if (dx || dy) mx = max(mx, (int)Sl[(y + dy) * L.w + x + dx]);
+                            if (mx > s) { status[L.base + y * L.w + x] = 0; continue; }
+                        }
+                    }
+                    xy.push_back((uint32_t)x | ((uint32_t)y << 16)); meta.push_back((uint32_t)l); row_count[L.row0 + y]++;
                 }
         }
         uint32_t run = 0;
@@ -176,11 +197,13 @@ struct Harness {
 extern "C" {
 
 // out: {x, y, size, response, layer, keep} per BRISK keypoint in reference order; returns the count
-int hh_detect(const uint8_t* diff, int w, int h, int reverse_rounds, float* out, int cap) {
+// mode: bit 0 = phase B rounds in reverse order, bit 1 = drop 8-neighbour losers inside their score tile before the candidate list
+int hh_detect(const uint8_t* diff, int w, int h, int mode, float* out, int cap) {
     Harness H;
     H.setup(w, h);
+    H.prune_tile_losers = (mode & 2) != 0;
     H.dense(diff);
-    H.sparse(reverse_rounds != 0);
+    H.sparse((mode & 1) != 0);
     int n = 0;
     for (size_t c = 0; c < H.xy.size(); c++) {
         if (!(H.flags[c] & ST_KEYPOINT)) continue;

@@ -70,6 +70,25 @@ def test_device_detector_source_on_tie_heavy_images(orc):
         assert util.kp_equal(util.harness_detect(img, reverse_rounds=True)[:, :5].copy(), want)
 
 
+@pytest.mark.parametrize("shape,seed", [((320, 240), 2), ((212, 163), 3), ((131, 70), 8)])
+def test_early_removal_of_tile_interior_losers_changes_no_keypoint(orc, shape, seed):
+    """k_scores drops a detector hit that has a strictly larger score among its 8 neighbours when the hit lies inside the
+    1-pixel frame of its 64 x 32 tile (status 0, never a candidate).  Same keypoints as the reference, also with phase B's
+    rounds reversed and on tie-heavy images, with the status map starting from stale bytes."""
+    w, h = shape
+    clip = mofreak_b200.synth_clip(w, h, 7, seed)
+    for _, d in util.diff_frames(clip):
+        want = orc.brisk(d)
+        for rev in (False, True):
+            assert util.kp_equal(util.harness_detect(d, reverse_rounds=rev, prune_tile_losers=True)[:, :5].copy(), want)
+    rng = np.random.default_rng(12 + seed)
+    img = (rng.integers(0, 4, (96, 160)) * 80).astype(np.uint8)
+    want = orc.brisk(img)
+    assert len(want) > 0
+    for rev in (False, True):
+        assert util.kp_equal(util.harness_detect(img, reverse_rounds=rev, prune_tile_losers=True)[:, :5].copy(), want)
+
+
 def test_device_layers_equal_oracle(orc):
     import ctypes as C
     L = util.harness()

@@ -68,12 +68,12 @@ def harness():
     return _harness
 
 
-def harness_detect(diff, reverse_rounds=False):
+def harness_detect(diff, reverse_rounds=False, prune_tile_losers=False):
     L = harness()
     diff = np.ascontiguousarray(diff, np.uint8)
     h, w = diff.shape
     out = np.zeros((1 << 16, 6), np.float32)
-    n = L.hh_detect(diff.ctypes.data_as(C.c_void_p), w, h, 1 if reverse_rounds else 0, out.ctypes.data_as(C.c_void_p), 1 << 16)
+    n = L.hh_detect(diff.ctypes.data_as(C.c_void_p), w, h, (1 if reverse_rounds else 0) | (2 if prune_tile_losers else 0), out.ctypes.data_as(C.c_void_p), 1 << 16)
     return out[:n].copy()
 
 
